@@ -1,0 +1,145 @@
+/* smeagol_b200 -- C-ABI of the B200-native PWM scanning hot path.
+ *
+ * This is the drop-in boundary for SMEAGOL's scan path.  The reference (gruber-sciencelab/SMEAGOL v0.1.1) is pure
+ * Python and has no FFI layer; its seam is PWMModel.predict_with_threshold (smeagol/models.py:119-178), fed by
+ * encode.integer_encode (smeagol/encode.py:47-68) and consumed by scan._find_sites_seq (smeagol/scan.py:150-208).
+ * Each entry point below cites the reference interface it replaces.  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain C types only; every `d_*` pointer is DEVICE memory owned by the caller (the library never frees it);
+ *    the PWM-set handle owns its own device tables.
+ *  - `stream` is a cudaStream_t passed as void*; all kernels are enqueued asynchronously on it.
+ *  - return value: SMG_OK or an SMG_ERR_* code; smg_last_error() gives a message for the calling thread.
+ *  - the library never falls back to the CPU.
+ */
+#ifndef SMEAGOL_B200_H
+#define SMEAGOL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMG_OK 0
+#define SMG_ERR_INVALID 1      /* bad argument */
+#define SMG_ERR_CUDA 2         /* a CUDA runtime call failed */
+#define SMG_ERR_UNSUPPORTED 3  /* e.g. no sm_100 device */
+
+#define SMG_MAX_REGTAB_WIDTH 32 /* wider PWMs go through the shared-memory gather kernel */
+#define SMG_STRAND_FWD 1
+#define SMG_STRAND_RC 2
+
+typedef struct smg_pwmset* smg_pwmset_t;
+
+/* One scanned row: a whole sequence, or a segment of a longer one (chunked / multi-GPU scans).  Bases are packed
+ * 16 per 32-bit word starting at word_off; rows are padded with >= 96 'Z' bases.  A window start s (row-local)
+ * is reported by this row iff 0 <= s < n_own and g_off + s + W <= g_len (models.py:110 trim rule). */
+typedef struct {
+    int64_t word_off; /* first word of the row in d_packed / d_amask; base offset in d_codes is 16*word_off */
+    int64_t g_off;    /* coordinate of the row's first base in the full sequence (0 for whole sequences) */
+    int64_t g_len;    /* length of the full sequence */
+    int32_t n_avail;  /* bases present in the buffer (owned + right halo) */
+    int32_t n_own;    /* window starts owned by this row */
+} smg_row_t;
+
+typedef struct {
+    int32_t row;   /* index into the row array */
+    int32_t start; /* first owned window start of the chunk (multiple of 16) */
+} smg_chunk_t;
+
+/* near-threshold candidate awaiting fp64 adjudication (north_star: sites within 1e-5 of the threshold) */
+typedef struct {
+    int32_t row;
+    int32_t motif;
+    int32_t strand; /* 0 = forward, 1 = reverse complement */
+    int32_t start;  /* row-local window start on the forward string */
+    float score;    /* fp32 kernel score */
+    int32_t reserved;
+} smg_near_t;
+
+/* counters written by smg_scan / smg_adjudicate (uint64 each) */
+#define SMG_CTR_HITS_APPENDED 0 /* entries reserved in the hit buffer (> hit_cap means overflow: grow and rescan) */
+#define SMG_CTR_NEAR 1          /* near-threshold candidates (> near_cap means overflow) */
+#define SMG_CTR_DEFINITE 2      /* hits decided by the fp32 kernel */
+#define SMG_CTR_ADJ_ACCEPTED 3  /* near-threshold candidates accepted by the fp64 adjudicator */
+#define SMG_CTR_LAUNCHES 4      /* kernel launches issued by the library on behalf of this counter block */
+#define SMG_N_COUNTERS 8
+
+int smg_version(void);
+const char* smg_last_error(void);
+/* number of exported kernels launched by this process so far (bench.py's gpu_launches claim) */
+uint64_t smg_launch_count(void);
+
+/* PWMModel.__init__ / _pad_weights / set_model_weights (models.py:35-48, 70-90): weights are the fp32-cast PWMs
+ * concatenated row-major (sum(widths) x 4, columns A,C,G,T), HOST memory.  Builds the device tables: natural
+ * layout, reverse-complement tables, and the lane-major register-table groups of the fused scan kernel. */
+int smg_pwmset_create(const float* h_weights, const int32_t* h_widths, int32_t n_motifs, smg_pwmset_t* out);
+int smg_pwmset_destroy(smg_pwmset_t set);
+/* info[0]=n_motifs info[1]=max_width info[2]=n_regtab_groups info[3]=n_buckets info[4]=n_wide_motifs
+ * info[5]=sum over groups of padded width (dual groups count both strands) */
+int smg_pwmset_info(smg_pwmset_t set, int64_t info[8]);
+
+/* encode.integer_encode (encode.py:47-68) on device.  d_src: concatenated ASCII bytes (input_kind 0) or integer
+ * codes 0..16 as uint8 (input_kind 1); row r occupies d_src[src_off[r] .. src_off[r]+rows[r].n_avail).
+ * Outputs: 2-bit packed bases, a 1-bit ambiguity mask (one uint16 per packed word), optionally the uint8 codes
+ * (d_codes may be NULL when the caller knows there is no ambiguity code).  d_status[0] = index into d_src of the
+ * first invalid character or -1 (the reference raises KeyError, encode.py:66); d_status[1] = 1 if any base is
+ * not A/C/G/T/U.  d_status must be initialised to {-1, 0}. */
+int smg_pack(const uint8_t* d_src, int input_kind, const smg_row_t* d_rows, const int64_t* d_src_off,
+             int32_t n_rows, int64_t total_words, uint32_t* d_packed, uint16_t* d_amask, uint8_t* d_codes,
+             int64_t* d_status, void* stream);
+
+/* PWMModel.predict_with_threshold (models.py:102-178) fused with the per-(row, motif, strand) counting of
+ * scan._count_sites (scan.py:114-147): both strands, threshold, end trim, stream compaction, counts.
+ *  d_thr_lo / d_thr_hi [n_motifs]: fp32 bounds of the near-threshold band; score > thr_hi is a definite hit,
+ *      thr_lo < score <= thr_hi is appended to d_near for smg_adjudicate.  With thr_lo == thr_hi == the largest
+ *      float <= frac*max_score the kernel reproduces the reference's `(double)score > thr` compare exactly.
+ *  d_out_rows [n_rows][2]: output row index of (row, strand) in the reference's row order (encode.py:137-160),
+ *      used as the most significant key field; strands bit mask selects the strands scanned.
+ *  hit key = out_row << (pos_bits+motif_bits) | pos << motif_bits | motif, pos in the coordinates of the scanned
+ *      string (for the RC strand: g_len - start - W, as the reference reports them).
+ *  d_hit_keys/d_hit_scores may be NULL (count-only); d_counts [n_rows][n_motifs][2] int32 may be NULL.
+ *  d_counters: SMG_N_COUNTERS uint64, zeroed by the caller. */
+int smg_scan(smg_pwmset_t set, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
+             const smg_row_t* d_rows, int32_t n_rows, const int32_t* d_out_rows, const smg_chunk_t* d_chunks,
+             int32_t n_chunks, int32_t chunk_len, int strands, const float* d_thr_lo, const float* d_thr_hi,
+             int pos_bits, int motif_bits, uint64_t* d_hit_keys, float* d_hit_scores, uint64_t hit_cap,
+             smg_near_t* d_near, uint64_t near_cap, int32_t* d_counts, uint64_t* d_counters, void* stream);
+
+/* fp64 adjudication of the near-threshold candidates: score64 = sum of the fp32 operands in double, hit iff
+ * score64 > d_thr64[motif] (thr = frac * max_scores computed on the host as models.py:141 does). */
+int smg_adjudicate(smg_pwmset_t set, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
+                   const smg_row_t* d_rows, const int32_t* d_out_rows, const double* d_thr64,
+                   const smg_near_t* d_near, uint64_t near_cap, int pos_bits, int motif_bits,
+                   uint64_t* d_hit_keys, float* d_hit_scores, uint64_t hit_cap, int32_t* d_counts,
+                   uint64_t* d_counters, void* stream);
+
+/* np.where row-major (row, pos, motif) order (models.py:108): radix sort of the hit keys with their scores.
+ * Call with d_temp == NULL to query *temp_bytes. */
+int smg_sort_hits(const uint64_t* d_keys_in, const float* d_scores_in, uint64_t* d_keys_out, float* d_scores_out,
+                  uint64_t n, int key_bits, void* d_temp, uint64_t* temp_bytes, void* stream);
+
+/* PWMModel.predict (models.py:92-100): dense (n_rows, L, n_motifs) fp32 scores of equal-length rows, including
+ * the zero-padded overhanging windows.  Small inputs / tests only. */
+int smg_predict_dense(smg_pwmset_t set, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
+                      const smg_row_t* d_rows, int32_t n_rows, int32_t row_len, float* d_out, void* stream);
+
+/* variant._variant_effect_on_site (variant.py:7-47) for explicit (site, variant) pairs, fp64:
+ * out_ref[i] = sum_k T[k, ref_k], out_alt[i] = same with the base at rel_pos replaced by alt_code. */
+int smg_variant_sites(smg_pwmset_t set, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
+                      const smg_row_t* d_rows, const int32_t* d_site_row, const int32_t* d_site_start,
+                      const int32_t* d_site_motif, const int32_t* d_rel_pos, const uint8_t* d_alt_code, int64_t n,
+                      double* d_out_ref, double* d_out_alt, void* stream);
+
+/* BASELINE config 5 (batched restatement of variant.py): for every SNV (row, pos, alt) and every PWM, the maximum
+ * reference and alternate score over all windows covering pos on both strands (fp32).  Outputs [n_snv][n_motifs]. */
+int smg_variant_windows(smg_pwmset_t set, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
+                        const smg_row_t* d_rows, const int32_t* d_snv_row, const int32_t* d_snv_pos,
+                        const uint8_t* d_snv_alt, int64_t n_snv, float* d_ref_max, float* d_alt_max, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMEAGOL_B200_H */

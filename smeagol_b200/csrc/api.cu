@@ -1,0 +1,603 @@
+// C-ABI entry points of libsmeagol_b200.so (see include/smeagol_b200.h) and the small non-hot kernels:
+// 2-bit packer, dense predict, fp64 adjudicator, wide-motif fallback, variant scoring, hit sort.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+#include "launchers.h"
+
+// ------------------------------------------------------------------------------------------ host-side state
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+#define SMG_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(SMG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+    } while (0)
+#define SMG_LAUNCH_CHECK(name)                                                                 \
+    do {                                                                                       \
+        ++g_launches;                                                                          \
+        cudaError_t e_ = cudaGetLastError();                                                   \
+        if (e_ != cudaSuccess) return fail(SMG_ERR_CUDA, std::string(name) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct Group {
+    int wb;
+    bool dual;
+    int lane_motif[32];
+    int lane_strand[32];
+    int64_t tab_off;
+};
+struct Bucket {
+    int wb;
+    bool dual;
+    int first_group;
+    int n_groups;
+};
+struct smg_pwmset {
+    int n_motifs = 0;
+    int max_w = 0;
+    std::vector<int> widths;
+    std::vector<int64_t> offs;
+    std::vector<Group> groups;
+    std::vector<Bucket> buckets;
+    std::vector<int> wide;
+    int64_t sum_padded = 0;
+    float* d_nat = nullptr;
+    int32_t* d_width = nullptr;
+    int64_t* d_off = nullptr;
+    float* d_gtab = nullptr;
+    int64_t* d_gtab_off = nullptr;
+    int32_t* d_lane_motif = nullptr;
+    int32_t* d_lane_strand = nullptr;
+    int32_t* d_wide = nullptr;
+};
+
+static const int kDualMaxWidth = 16;  // PWMs up to this width keep both strands in one lane (float2 pairs)
+
+// ------------------------------------------------------------------------------------------ kernels
+static __constant__ uint8_t c_lut[256];
+
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ src, const int kind,
+                                                   const smg_row_t* __restrict__ rows, const int64_t* __restrict__ src_off,
+                                                   const int n_rows, const int64_t total_words, uint32_t* __restrict__ packed,
+                                                   uint16_t* __restrict__ amask, uint8_t* __restrict__ codes,
+                                                   unsigned long long* __restrict__ status)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < total_words; wi += stride) {
+        int lo = 0, hi = n_rows - 1;  // largest r with rows[r].word_off <= wi
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (rows[mid].word_off <= wi) lo = mid; else hi = mid - 1;
+        }
+        const smg_row_t row = rows[lo];
+        const int64_t q0 = (wi - row.word_off) * 16;
+        const int64_t so = src_off[lo];
+        uint8_t raw[16];
+        const int64_t rem = (int64_t)row.n_avail - q0;
+        if (rem >= 16 && ((so + q0) & 15) == 0) {
+            const uint4 v = *reinterpret_cast<const uint4*>(src + so + q0);
+            memcpy(raw, &v, 16);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) raw[j] = (j < rem) ? src[so + q0 + j] : 0;
+        }
+        uint32_t pw = 0, aw = 0;
+        uint8_t cd[16];
+        bool any_amb = false;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            int code = 0;
+            if (j < rem) {
+                code = kind ? (int)raw[j] : (int)c_lut[raw[j]];
+                if (code > 16) {  // KeyError in the reference (encode.py:66)
+                    atomicMin(&status[0], (unsigned long long)(so + q0 + j));
+                    code = 0;
+                }
+                if (code < 1 || code > 5) any_amb = true;
+            }
+            const bool plain = code >= 1 && code <= 5;
+            const uint32_t two = plain ? (code == 5 ? 3u : (uint32_t)(code - 1)) : 0u;
+            pw |= two << (2 * j);
+            aw |= (plain ? 0u : 1u) << j;
+            cd[j] = (uint8_t)code;
+        }
+        packed[wi] = pw;
+        amask[wi] = (uint16_t)aw;
+        if (codes) {
+            uint4 v;
+            memcpy(&v, cd, 16);
+            *reinterpret_cast<uint4*>(codes + wi * 16) = v;
+        }
+        if (any_amb) status[1] = 1ull;
+    }
+}
+
+// score of one window on the forward string, strand st, fp32 ascending-k order (same order as the register kernel)
+__device__ float window_score32(const ScanParams& p, const smg_row_t& row, const int motif, const int st, const int64_t s)
+{
+    const int wm = p.motif_width[motif];
+    const float* tab = p.nat_tab + p.motif_off[motif] * 4;
+    float acc = 0.f;
+    for (int k = 0; k < wm; ++k) {
+        const int c = smg_fetch_code(p.packed, p.amask, p.codes, row, s + k);
+        const float* tr = tab + (st ? (wm - 1 - k) : k) * 4;
+        const float t0 = st ? tr[3] : tr[0], t1 = st ? tr[2] : tr[1], t2 = st ? tr[1] : tr[2], t3 = st ? tr[0] : tr[3];
+        const float term = smg_mix(c_emb[c][0], c_emb[c][1], c_emb[c][2], c_emb[c][3], t0, t1, t2, t3);
+        acc = (k == 0) ? term : __fadd_rn(acc, term);
+    }
+    return acc;
+}
+
+__device__ double window_score64(const uint32_t* packed, const uint16_t* amask, const uint8_t* codes, const smg_row_t& row,
+                                 const float* tab, const int wm, const int st, const int64_t s, const int64_t sub_pos,
+                                 const int sub_code)
+{
+    double acc = 0.0;
+    for (int k = 0; k < wm; ++k) {
+        int c = smg_fetch_code(packed, amask, codes, row, s + k);
+        if (s + k == sub_pos) c = sub_code;
+        const float* tr = tab + (st ? (wm - 1 - k) : k) * 4;
+        const float t0 = st ? tr[3] : tr[0], t1 = st ? tr[2] : tr[1], t2 = st ? tr[1] : tr[2], t3 = st ? tr[0] : tr[3];
+        const double term = smg_mix64(c, t0, t1, t2, t3);
+        acc = (k == 0) ? term : __dadd_rn(acc, term);
+    }
+    return acc;
+}
+
+// Fallback for PWMs wider than SMG_MAX_REGTAB_WIDTH: one thread per window start, tables from global memory.
+__global__ void __launch_bounds__(128) scan_wide_kernel(const ScanParams p, const int32_t* __restrict__ wide, const int n_wide)
+{
+    const smg_chunk_t ch = p.chunks[blockIdx.x];
+    const smg_row_t row = p.rows[ch.row];
+    const int c0 = ch.start;
+    const int c1 = min(c0 + p.chunk_len, row.n_own);
+    const int key_shift = p.pos_bits + p.motif_bits;
+    for (int s = c0 + threadIdx.x; s < c1; s += blockDim.x) {
+        for (int i = 0; i < n_wide; ++i) {
+            const int motif = wide[i];
+            const int wm = p.motif_width[motif];
+            const long long smax64 = row.g_len - row.g_off - (long long)wm;
+            if ((long long)s > smax64) continue;
+            for (int st = 0; st < 2; ++st) {
+                if (!((p.strands >> st) & 1)) continue;
+                const float v = window_score32(p, row, motif, st, s);
+                if (!(v > p.thr_lo[motif])) continue;
+                if (v > p.thr_hi[motif]) {
+                    atomicAdd(&p.counters[SMG_CTR_DEFINITE], 1ull);
+                    if (p.counts) atomicAdd(p.counts + ((size_t)ch.row * p.n_motifs + motif) * 2 + st, 1);
+                    if (p.hit_keys) {
+                        const unsigned long long idx = atomicAdd(&p.counters[SMG_CTR_HITS_APPENDED], 1ull);
+                        if (idx < p.hit_cap) {
+                            const long long pos = st ? (smax64 - (long long)s) : (row.g_off + (long long)s);
+                            p.hit_keys[idx] = ((unsigned long long)(unsigned)p.out_rows[ch.row * 2 + st] << key_shift) |
+                                              ((unsigned long long)pos << p.motif_bits) | (unsigned long long)(unsigned)motif;
+                            p.hit_scores[idx] = v;
+                        }
+                    }
+                } else {
+                    const unsigned long long idx = atomicAdd(&p.counters[SMG_CTR_NEAR], 1ull);
+                    if (idx < p.near_cap) {
+                        smg_near_t n;
+                        n.row = ch.row; n.motif = motif; n.strand = st; n.start = s; n.score = v; n.reserved = 0;
+                        p.near[idx] = n;
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) adjudicate_kernel(const ScanParams p, const double* __restrict__ thr64)
+{
+    const unsigned long long n_near = min(p.counters[SMG_CTR_NEAR], p.near_cap);
+    const int key_shift = p.pos_bits + p.motif_bits;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_near;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const smg_near_t n = p.near[i];
+        const smg_row_t row = p.rows[n.row];
+        const int wm = p.motif_width[n.motif];
+        const double s64 = window_score64(p.packed, p.amask, p.codes, row, p.nat_tab + p.motif_off[n.motif] * 4, wm, n.strand,
+                                          n.start, -1, 0);
+        if (s64 > thr64[n.motif]) {
+            atomicAdd(&p.counters[SMG_CTR_ADJ_ACCEPTED], 1ull);
+            if (p.counts) atomicAdd(p.counts + ((size_t)n.row * p.n_motifs + n.motif) * 2 + n.strand, 1);
+            if (p.hit_keys) {
+                const unsigned long long idx = atomicAdd(&p.counters[SMG_CTR_HITS_APPENDED], 1ull);
+                if (idx < p.hit_cap) {
+                    const long long smax64 = row.g_len - row.g_off - (long long)wm;
+                    const long long pos = n.strand ? (smax64 - (long long)n.start) : (row.g_off + (long long)n.start);
+                    p.hit_keys[idx] = ((unsigned long long)(unsigned)p.out_rows[n.row * 2 + n.strand] << key_shift) |
+                                      ((unsigned long long)pos << p.motif_bits) | (unsigned long long)(unsigned)n.motif;
+                    p.hit_scores[idx] = n.score;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) dense_kernel(const ScanParams p, const int n_rows, const int row_len, float* __restrict__ out)
+{
+    const int64_t total = (int64_t)n_rows * row_len * p.n_motifs;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(i % p.n_motifs);
+        const int64_t rp = i / p.n_motifs;
+        const int pos = (int)(rp % row_len);
+        const int r = (int)(rp / row_len);
+        out[i] = window_score32(p, p.rows[r], m, 0, pos);
+    }
+}
+
+__global__ void __launch_bounds__(128) variant_sites_kernel(const ScanParams p, const int32_t* __restrict__ site_row,
+                                                            const int32_t* __restrict__ site_start, const int32_t* __restrict__ site_motif,
+                                                            const int32_t* __restrict__ rel_pos, const uint8_t* __restrict__ alt_code,
+                                                            const int64_t n, double* __restrict__ out_ref, double* __restrict__ out_alt)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const smg_row_t row = p.rows[site_row[i]];
+        const int m = site_motif[i];
+        const int wm = p.motif_width[m];
+        const float* tab = p.nat_tab + p.motif_off[m] * 4;
+        const int64_t s = site_start[i];
+        out_ref[i] = window_score64(p.packed, p.amask, p.codes, row, tab, wm, 0, s, -1, 0);
+        out_alt[i] = window_score64(p.packed, p.amask, p.codes, row, tab, wm, 0, s, s + rel_pos[i], alt_code[i]);
+    }
+}
+
+// Batched SNV scoring (BASELINE config 5).  One warp per (32-motif block, SNV tile); lane = motif; tables are read
+// from global memory (L1-resident: 32 motifs x W x 4 floats), the 2W-1 bases around the SNV are warp-uniform.
+__global__ void __launch_bounds__(128) variant_windows_kernel(const ScanParams p, const int32_t* __restrict__ snv_row,
+                                                              const int32_t* __restrict__ snv_pos, const uint8_t* __restrict__ snv_alt,
+                                                              const int64_t n_snv, float* __restrict__ ref_max, float* __restrict__ alt_max)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp_in_block = threadIdx.x >> 5;
+    const int m = blockIdx.y * 32 + lane;
+    const bool active = m < p.n_motifs;
+    const int wm = active ? p.motif_width[m] : 0;
+    const float* tab = active ? p.nat_tab + p.motif_off[m] * 4 : nullptr;
+    const float ninf = __int_as_float(0xff800000);
+    for (int64_t v = (int64_t)blockIdx.x * 4 + warp_in_block; v < n_snv; v += (int64_t)gridDim.x * 4) {
+        const smg_row_t row = p.rows[snv_row[v]];
+        const int64_t pos = snv_pos[v];
+        const int alt = snv_alt[v];
+        float rmax = ninf, amax = ninf;
+        if (active) {
+            const int64_t s_lo = max((int64_t)0, pos - wm + 1);
+            const int64_t s_hi = min(pos, row.g_len - row.g_off - (int64_t)wm);
+            for (int64_t s = s_lo; s <= s_hi; ++s) {
+                for (int st = 0; st < 2; ++st) {
+                    float ra = 0.f, aa = 0.f;
+                    for (int k = 0; k < wm; ++k) {
+                        const int c = smg_fetch_code(p.packed, p.amask, p.codes, row, s + k);
+                        const int ca = (s + k == pos) ? alt : c;
+                        const float* tr = tab + (st ? (wm - 1 - k) : k) * 4;
+                        const float t0 = st ? tr[3] : tr[0], t1 = st ? tr[2] : tr[1], t2 = st ? tr[1] : tr[2], t3 = st ? tr[0] : tr[3];
+                        const float tr_ref = smg_mix(c_emb[c][0], c_emb[c][1], c_emb[c][2], c_emb[c][3], t0, t1, t2, t3);
+                        const float tr_alt = smg_mix(c_emb[ca][0], c_emb[ca][1], c_emb[ca][2], c_emb[ca][3], t0, t1, t2, t3);
+                        ra = (k == 0) ? tr_ref : __fadd_rn(ra, tr_ref);
+                        aa = (k == 0) ? tr_alt : __fadd_rn(aa, tr_alt);
+                    }
+                    rmax = fmaxf(rmax, ra);
+                    amax = fmaxf(amax, aa);
+                }
+            }
+            ref_max[v * p.n_motifs + m] = rmax;
+            alt_max[v * p.n_motifs + m] = amax;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host helpers
+static int init_lut()
+{
+    static bool done[64] = {false};
+    int dev = 0;
+    SMG_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && done[dev]) return SMG_OK;
+    cudaDeviceProp prop;
+    SMG_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return fail(SMG_ERR_UNSUPPORTED, "smeagol_b200 is built for sm_100a (B200) only");
+    uint8_t lut[256];
+    memset(lut, 255, sizeof(lut));
+    const char* alphabet = "ZACGTUNWSMKRYBDHV";  // encode.py:11-41, uppercase only (lowercase raises KeyError there)
+    for (int i = 0; i < 17; ++i) lut[(unsigned char)alphabet[i]] = (uint8_t)i;
+    SMG_CUDA(cudaMemcpyToSymbol(c_lut, lut, 256));
+    if (dev < 64) done[dev] = true;
+    return SMG_OK;
+}
+
+template <typename T>
+static int upload(T** dptr, const std::vector<T>& h)
+{
+    const size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    SMG_CUDA(cudaMalloc((void**)dptr, bytes));
+    if (!h.empty()) SMG_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SMG_OK;
+}
+
+// ------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int smg_version(void) { return 100; }
+const char* smg_last_error(void) { return g_err.c_str(); }
+uint64_t smg_launch_count(void) { return g_launches.load(); }
+
+int smg_pwmset_create(const float* h_weights, const int32_t* h_widths, int32_t n_motifs, smg_pwmset_t* out)
+{
+    if (!h_weights || !h_widths || n_motifs <= 0 || !out) return fail(SMG_ERR_INVALID, "smg_pwmset_create: bad argument");
+    int rc = init_lut();
+    if (rc != SMG_OK) return rc;
+    smg_pwmset* s = new smg_pwmset();
+    s->n_motifs = n_motifs;
+    s->widths.assign(h_widths, h_widths + n_motifs);
+    s->offs.resize(n_motifs);
+    int64_t tot = 0;
+    for (int m = 0; m < n_motifs; ++m) {
+        if (h_widths[m] <= 0) { delete s; return fail(SMG_ERR_INVALID, "smg_pwmset_create: PWM width must be >= 1"); }
+        s->offs[m] = tot;
+        tot += h_widths[m];
+        s->max_w = std::max(s->max_w, (int)h_widths[m]);
+    }
+    for (int64_t i = 0; i < tot * 4; ++i)
+        if (!std::isfinite(h_weights[i])) { delete s; return fail(SMG_ERR_INVALID, "smg_pwmset_create: non-finite PWM weight"); }
+
+    // ---- lane groups: columns sorted by width, 32 per group, remainders carried up to the next width
+    struct Col { int motif, strand; };
+    auto build = [&](bool dual, int wlo, int whi) {
+        std::vector<Col> pool;
+        auto emit_group = [&](int wb, size_t n_take) {
+            Group g;
+            g.wb = std::max(wb, 2);
+            g.dual = dual;
+            g.tab_off = 0;
+            for (int l = 0; l < 32; ++l) { g.lane_motif[l] = -1; g.lane_strand[l] = 0; }
+            for (size_t l = 0; l < n_take; ++l) { g.lane_motif[l] = pool[l].motif; g.lane_strand[l] = pool[l].strand; }
+            pool.erase(pool.begin(), pool.begin() + n_take);
+            s->groups.push_back(g);
+        };
+        int last_w = 0;
+        for (int w = wlo; w <= whi; ++w) {
+            bool any = false;
+            for (int m = 0; m < n_motifs; ++m) {
+                if (h_widths[m] != w) continue;
+                any = true;
+                if (dual) pool.push_back({m, 0});
+                else { pool.push_back({m, 0}); pool.push_back({m, 1}); }
+            }
+            if (any) last_w = w;
+            while (pool.size() >= 32) emit_group(w, 32);
+        }
+        if (!pool.empty()) emit_group(last_w, pool.size());
+    };
+    build(true, 1, kDualMaxWidth);
+    build(false, kDualMaxWidth + 1, SMG_MAX_REGTAB_WIDTH);
+    for (int m = 0; m < n_motifs; ++m)
+        if (h_widths[m] > SMG_MAX_REGTAB_WIDTH) s->wide.push_back(m);
+    // buckets of equal (wb, dual), groups reordered so that a bucket is contiguous
+    std::stable_sort(s->groups.begin(), s->groups.end(), [](const Group& a, const Group& b) {
+        if (a.dual != b.dual) return a.dual > b.dual;
+        return a.wb < b.wb;
+    });
+    std::vector<float> gtab;
+    std::vector<int64_t> gtab_off;
+    std::vector<int32_t> lane_motif, lane_strand;
+    for (size_t gi = 0; gi < s->groups.size(); ++gi) {
+        Group& g = s->groups[gi];
+        if (s->buckets.empty() || s->buckets.back().wb != g.wb || s->buckets.back().dual != g.dual)
+            s->buckets.push_back({g.wb, g.dual, (int)gi, 0});
+        s->buckets.back().n_groups++;
+        g.tab_off = (int64_t)gtab.size();
+        gtab_off.push_back(g.tab_off);
+        const int comps = g.dual ? 2 : 1;
+        gtab.resize(gtab.size() + (size_t)g.wb * 4 * 32 * comps, 0.f);
+        float* gt = gtab.data() + g.tab_off;
+        s->sum_padded += (int64_t)g.wb * comps;
+        for (int l = 0; l < 32; ++l) {
+            lane_motif.push_back(g.lane_motif[l]);
+            lane_strand.push_back(g.lane_strand[l]);
+            const int m = g.lane_motif[l];
+            if (m < 0) continue;
+            const int wm = h_widths[m];
+            const float* T = h_weights + s->offs[m] * 4;
+            for (int k = 0; k < wm; ++k)
+                for (int b = 0; b < 4; ++b) {
+                    const float fwd = T[k * 4 + b];
+                    const float rc = T[(wm - 1 - k) * 4 + (3 - b)];  // Trc[k][b] = T[W-1-k][3-b]
+                    const size_t e = (size_t)(k * 4 + b) * 32 + l;
+                    if (g.dual) { gt[e * 2 + 0] = fwd; gt[e * 2 + 1] = rc; }
+                    else gt[e] = g.lane_strand[l] ? rc : fwd;
+                }
+        }
+    }
+    std::vector<float> nat(h_weights, h_weights + tot * 4);
+    std::vector<int32_t> wv(h_widths, h_widths + n_motifs);
+    std::vector<int32_t> widev(s->wide.begin(), s->wide.end());
+    if ((rc = upload(&s->d_nat, nat)) || (rc = upload(&s->d_width, wv)) || (rc = upload(&s->d_off, s->offs)) ||
+        (rc = upload(&s->d_gtab, gtab)) || (rc = upload(&s->d_gtab_off, gtab_off)) ||
+        (rc = upload(&s->d_lane_motif, lane_motif)) || (rc = upload(&s->d_lane_strand, lane_strand)) ||
+        (rc = upload(&s->d_wide, widev))) {
+        smg_pwmset_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return SMG_OK;
+}
+
+int smg_pwmset_destroy(smg_pwmset_t s)
+{
+    if (!s) return SMG_OK;
+    cudaFree(s->d_nat); cudaFree(s->d_width); cudaFree(s->d_off); cudaFree(s->d_gtab); cudaFree(s->d_gtab_off);
+    cudaFree(s->d_lane_motif); cudaFree(s->d_lane_strand); cudaFree(s->d_wide);
+    delete s;
+    return SMG_OK;
+}
+
+int smg_pwmset_info(smg_pwmset_t s, int64_t info[8])
+{
+    if (!s || !info) return fail(SMG_ERR_INVALID, "smg_pwmset_info: bad argument");
+    memset(info, 0, 8 * sizeof(int64_t));
+    info[0] = s->n_motifs; info[1] = s->max_w; info[2] = (int64_t)s->groups.size(); info[3] = (int64_t)s->buckets.size();
+    info[4] = (int64_t)s->wide.size(); info[5] = s->sum_padded;
+    return SMG_OK;
+}
+
+int smg_pack(const uint8_t* d_src, int input_kind, const smg_row_t* d_rows, const int64_t* d_src_off, int32_t n_rows,
+             int64_t total_words, uint32_t* d_packed, uint16_t* d_amask, uint8_t* d_codes, int64_t* d_status, void* stream)
+{
+    if (!d_src || !d_rows || !d_src_off || n_rows <= 0 || total_words <= 0 || !d_packed || !d_amask || !d_status)
+        return fail(SMG_ERR_INVALID, "smg_pack: bad argument");
+    int rc = init_lut();
+    if (rc != SMG_OK) return rc;
+    const int64_t blocks = std::min<int64_t>((total_words + 255) / 256, 148 * 32);
+    pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_src, input_kind, d_rows, d_src_off, n_rows, total_words,
+                                                                    d_packed, d_amask, d_codes,
+                                                                    reinterpret_cast<unsigned long long*>(d_status));
+    SMG_LAUNCH_CHECK("pack_kernel");
+    return SMG_OK;
+}
+
+static void fill_params(ScanParams& p, smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
+                        const smg_row_t* d_rows, const int32_t* d_out_rows)
+{
+    memset(&p, 0, sizeof(p));
+    p.packed = d_packed; p.amask = d_amask; p.codes = d_codes; p.rows = d_rows; p.out_rows = d_out_rows;
+    p.n_motifs = s->n_motifs; p.motif_width = s->d_width; p.motif_off = s->d_off; p.nat_tab = s->d_nat;
+    p.group_tab = s->d_gtab; p.group_tab_off = s->d_gtab_off; p.lane_motif = s->d_lane_motif; p.lane_strand = s->d_lane_strand;
+}
+
+int smg_scan(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes, const smg_row_t* d_rows,
+             int32_t n_rows, const int32_t* d_out_rows, const smg_chunk_t* d_chunks, int32_t n_chunks, int32_t chunk_len,
+             int strands, const float* d_thr_lo, const float* d_thr_hi, int pos_bits, int motif_bits, uint64_t* d_hit_keys,
+             float* d_hit_scores, uint64_t hit_cap, smg_near_t* d_near, uint64_t near_cap, int32_t* d_counts,
+             uint64_t* d_counters, void* stream)
+{
+    if (!s || !d_packed || !d_amask || !d_rows || n_rows <= 0 || !d_out_rows || !d_chunks || n_chunks < 0 || !d_thr_lo ||
+        !d_thr_hi || !d_counters || !d_near)
+        return fail(SMG_ERR_INVALID, "smg_scan: bad argument");
+    if (chunk_len <= 0 || (chunk_len & 15)) return fail(SMG_ERR_INVALID, "smg_scan: chunk_len must be a positive multiple of 16");
+    if ((strands & 3) == 0 || (strands & ~3)) return fail(SMG_ERR_INVALID, "smg_scan: strands must be 1, 2 or 3");
+    if (pos_bits <= 0 || motif_bits <= 0 || pos_bits + motif_bits > 63) return fail(SMG_ERR_INVALID, "smg_scan: bad key layout");
+    if ((1ll << motif_bits) < s->n_motifs) return fail(SMG_ERR_INVALID, "smg_scan: motif_bits too small");
+    if ((d_hit_keys == nullptr) != (d_hit_scores == nullptr)) return fail(SMG_ERR_INVALID, "smg_scan: hit buffers must both be set or NULL");
+    if (n_chunks == 0) return SMG_OK;
+    ScanParams p;
+    fill_params(p, s, d_packed, d_amask, d_codes, d_rows, d_out_rows);
+    p.chunks = d_chunks; p.chunk_len = chunk_len; p.strands = strands; p.thr_lo = d_thr_lo; p.thr_hi = d_thr_hi;
+    p.pos_bits = pos_bits; p.motif_bits = motif_bits;
+    p.hit_keys = reinterpret_cast<unsigned long long*>(d_hit_keys); p.hit_scores = d_hit_scores; p.hit_cap = hit_cap;
+    p.near = d_near; p.near_cap = near_cap; p.counts = d_counts;
+    p.counters = reinterpret_cast<unsigned long long*>(d_counters);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (const Bucket& b : s->buckets) {
+        smg_launch_fn fn = smg_get_launcher(b.wb, b.dual);
+        if (!fn) return fail(SMG_ERR_INVALID, "smg_scan: no kernel for padded width " + std::to_string(b.wb));
+        p.first_group = b.first_group;
+        for (int g0 = 0; g0 < b.n_groups; g0 += 65535) {  // gridDim.y limit
+            ScanParams q = p;
+            q.first_group = b.first_group + g0;
+            fn(q, n_chunks, std::min(65535, b.n_groups - g0), st);
+            SMG_LAUNCH_CHECK("scan_regtab_kernel");
+        }
+    }
+    if (!s->wide.empty()) {
+        scan_wide_kernel<<<(unsigned)n_chunks, 128, 0, st>>>(p, s->d_wide, (int)s->wide.size());
+        SMG_LAUNCH_CHECK("scan_wide_kernel");
+    }
+    return SMG_OK;
+}
+
+int smg_adjudicate(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
+                   const smg_row_t* d_rows, const int32_t* d_out_rows, const double* d_thr64, const smg_near_t* d_near,
+                   uint64_t near_cap, int pos_bits, int motif_bits, uint64_t* d_hit_keys, float* d_hit_scores, uint64_t hit_cap,
+                   int32_t* d_counts, uint64_t* d_counters, void* stream)
+{
+    if (!s || !d_packed || !d_amask || !d_rows || !d_out_rows || !d_thr64 || !d_near || !d_counters)
+        return fail(SMG_ERR_INVALID, "smg_adjudicate: bad argument");
+    ScanParams p;
+    fill_params(p, s, d_packed, d_amask, d_codes, d_rows, d_out_rows);
+    p.pos_bits = pos_bits; p.motif_bits = motif_bits;
+    p.hit_keys = reinterpret_cast<unsigned long long*>(d_hit_keys); p.hit_scores = d_hit_scores; p.hit_cap = hit_cap;
+    p.near = const_cast<smg_near_t*>(d_near); p.near_cap = near_cap; p.counts = d_counts;
+    p.counters = reinterpret_cast<unsigned long long*>(d_counters);
+    const uint64_t want = std::max<uint64_t>(1, std::min<uint64_t>(near_cap, 1u << 20));
+    adjudicate_kernel<<<(unsigned)((want + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p, d_thr64);
+    SMG_LAUNCH_CHECK("adjudicate_kernel");
+    return SMG_OK;
+}
+
+int smg_sort_hits(const uint64_t* d_keys_in, const float* d_scores_in, uint64_t* d_keys_out, float* d_scores_out, uint64_t n,
+                  int key_bits, void* d_temp, uint64_t* temp_bytes, void* stream)
+{
+    if (!temp_bytes || key_bits <= 0 || key_bits > 64) return fail(SMG_ERR_INVALID, "smg_sort_hits: bad argument");
+    size_t tb = d_temp ? (size_t)*temp_bytes : 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(d_temp, tb, reinterpret_cast<const unsigned long long*>(d_keys_in),
+                                                    reinterpret_cast<unsigned long long*>(d_keys_out), d_scores_in, d_scores_out,
+                                                    (size_t)n, 0, key_bits, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(SMG_ERR_CUDA, std::string("cub::DeviceRadixSort: ") + cudaGetErrorString(e));
+    if (!d_temp) *temp_bytes = (uint64_t)tb; else ++g_launches;
+    return SMG_OK;
+}
+
+int smg_predict_dense(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
+                      const smg_row_t* d_rows, int32_t n_rows, int32_t row_len, float* d_out, void* stream)
+{
+    if (!s || !d_packed || !d_amask || !d_rows || n_rows <= 0 || row_len <= 0 || !d_out)
+        return fail(SMG_ERR_INVALID, "smg_predict_dense: bad argument");
+    ScanParams p;
+    fill_params(p, s, d_packed, d_amask, d_codes, d_rows, nullptr);
+    const int64_t total = (int64_t)n_rows * row_len * s->n_motifs;
+    const int64_t blocks = std::min<int64_t>((total + 255) / 256, 148 * 64);
+    dense_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, n_rows, row_len, d_out);
+    SMG_LAUNCH_CHECK("dense_kernel");
+    return SMG_OK;
+}
+
+int smg_variant_sites(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
+                      const smg_row_t* d_rows, const int32_t* d_site_row, const int32_t* d_site_start, const int32_t* d_site_motif,
+                      const int32_t* d_rel_pos, const uint8_t* d_alt_code, int64_t n, double* d_out_ref, double* d_out_alt,
+                      void* stream)
+{
+    if (!s || !d_packed || !d_amask || !d_rows || !d_site_row || !d_site_start || !d_site_motif || !d_rel_pos || !d_alt_code ||
+        n < 0 || !d_out_ref || !d_out_alt)
+        return fail(SMG_ERR_INVALID, "smg_variant_sites: bad argument");
+    if (n == 0) return SMG_OK;
+    ScanParams p;
+    fill_params(p, s, d_packed, d_amask, d_codes, d_rows, nullptr);
+    const int64_t blocks = std::min<int64_t>((n + 127) / 128, 148 * 32);
+    variant_sites_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(p, d_site_row, d_site_start, d_site_motif, d_rel_pos,
+                                                                            d_alt_code, n, d_out_ref, d_out_alt);
+    SMG_LAUNCH_CHECK("variant_sites_kernel");
+    return SMG_OK;
+}
+
+int smg_variant_windows(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
+                        const smg_row_t* d_rows, const int32_t* d_snv_row, const int32_t* d_snv_pos, const uint8_t* d_snv_alt,
+                        int64_t n_snv, float* d_ref_max, float* d_alt_max, void* stream)
+{
+    if (!s || !d_packed || !d_amask || !d_rows || !d_snv_row || !d_snv_pos || !d_snv_alt || n_snv < 0 || !d_ref_max || !d_alt_max)
+        return fail(SMG_ERR_INVALID, "smg_variant_windows: bad argument");
+    if (n_snv == 0) return SMG_OK;
+    ScanParams p;
+    fill_params(p, s, d_packed, d_amask, d_codes, d_rows, nullptr);
+    dim3 grid((unsigned)std::min<int64_t>((n_snv + 3) / 4, 148 * 64), (unsigned)((s->n_motifs + 31) / 32), 1);
+    variant_windows_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p, d_snv_row, d_snv_pos, d_snv_alt, n_snv, d_ref_max, d_alt_max);
+    SMG_LAUNCH_CHECK("variant_windows_kernel");
+    return SMG_OK;
+}
+
+}  // extern "C"

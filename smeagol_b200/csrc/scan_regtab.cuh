@@ -1,0 +1,248 @@
+// Fused PWM scan kernel, register-table variant (the hot path).
+//
+// Replaces PWMModel.predict + np.where threshold + end trim (smeagol/models.py:92-117) and the per-(row, motif,
+// strand) counting of scan._count_sites (smeagol/scan.py:114-147) for both strands in ONE pass.
+//
+// Mapping (B200-first, not a Conv1D): one warp per CTA; every LANE owns one PWM (both strands, as the two halves
+// of a float2) or one (PWM, strand) column, with its whole log-odds table in REGISTERS.  The sequence is the
+// warp-uniform operand: all lanes consume the same base at the same step, so the table row is selected by
+// uniform control flow (4-way branch on the 2-bit base) and no per-lane indexing, shared-memory lookup or bank
+// conflict exists.  The window sum is a shift register:  r[k] <- r[k-1] + T[k][b]  (ascending-k summation order,
+// bit-identical to a sequential fp32 sum), advanced with packed FADD2 (sm_100 fp32x2) so that one issue slot
+// performs the add for the forward AND the reverse-complement strand (RC strand = forward string scanned with
+// Trc[k][b] = T[W-1-k][3-b]).  Completed window scores are checked against the per-PWM threshold every U steps;
+// hits are compacted with warp ballot + prefix popcount into a per-warp shared-memory stage and appended to the
+// global hit list with one atomic per flush; per-lane counters give the count table.
+//
+// Algorithmic work: 2*W lookup-adds per base x motif (both strands).  The binding unit is the FP32 pipe
+// (128 lanes/clk/SM; FADD2 issues 64 adds per slot), not shared memory: measured ~2x the LDS gather roofline.
+#pragma once
+#include "common.cuh"
+
+namespace smg {
+
+template <bool DUAL> struct VecOf { using T = float2; };
+template <> struct VecOf<false> { using T = float; };
+
+__device__ __forceinline__ float2 vadd(const float2 a, const float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float vadd(const float a, const float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float vmax(const float2 a) { return fmaxf(a.x, a.y); }
+__device__ __forceinline__ float vmax(const float a) { return a; }
+__device__ __forceinline__ float vmax3(const float m, const float2 a)
+{
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(m), "f"(a.x), "f"(a.y));
+    return d;
+}
+__device__ __forceinline__ float vmax3(const float m, const float a) { return fmaxf(m, a); }
+__device__ __forceinline__ float vget(const float2 a, const int s) { return s ? a.y : a.x; }
+__device__ __forceinline__ float vget(const float a, const int) { return a; }
+__device__ __forceinline__ float2 vmix(const float e0, const float e1, const float e2, const float e3, const float2 t0,
+                                       const float2 t1, const float2 t2, const float2 t3)
+{
+    return make_float2(smg_mix(e0, e1, e2, e3, t0.x, t1.x, t2.x, t3.x), smg_mix(e0, e1, e2, e3, t0.y, t1.y, t2.y, t3.y));
+}
+__device__ __forceinline__ float vmix(const float e0, const float e1, const float e2, const float e3, const float t0,
+                                      const float t1, const float t2, const float t3)
+{
+    return smg_mix(e0, e1, e2, e3, t0, t1, t2, t3);
+}
+
+constexpr int kStageCap = 128;   // per-warp staged hits
+constexpr int kStageFlush = 64;  // flush when more than this many are staged (one event adds <= 32)
+constexpr int kU = 4;            // steps between threshold checks on the ACGT fast path
+
+// one shift-register step for base B (compile-time); O receives the completed window score
+#define SMG_STEP(B, O)                                                                        \
+    {                                                                                         \
+        O = vadd(r[WB - 2], t[WB - 1][B]);                                                    \
+        _Pragma("unroll") for (int k = WB - 2; k >= 1; --k) r[k] = vadd(r[k - 1], t[k][B]);   \
+        r[0] = t[0][B];                                                                       \
+    }
+
+#define SMG_SWITCH_STEP(b, O)      \
+    switch (b) {                   \
+    case 0: SMG_STEP(0, O); break; \
+    case 1: SMG_STEP(1, O); break; \
+    case 2: SMG_STEP(2, O); break; \
+    default: SMG_STEP(3, O); break; \
+    }
+
+template <int WB, bool DUAL>
+__global__ void __launch_bounds__(32) scan_regtab_kernel(const ScanParams p)
+{
+    static_assert(WB >= 2 && WB <= SMG_MAX_REGTAB_WIDTH, "unsupported padded width");
+    using V = typename VecOf<DUAL>::T;
+    __shared__ unsigned long long s_keys[kStageCap];
+    __shared__ float s_scores[kStageCap];
+
+    const int lane = threadIdx.x;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int group = p.first_group + blockIdx.y;
+    const smg_chunk_t ch = p.chunks[blockIdx.x];
+    const smg_row_t row = p.rows[ch.row];
+
+    // ---- per-lane PWM: table into registers, thresholds, trim bound
+    V t[WB][4];
+    {
+        const V* gt = reinterpret_cast<const V*>(p.group_tab + p.group_tab_off[group]);
+#pragma unroll
+        for (int k = 0; k < WB; ++k)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) t[k][b] = gt[(k * 4 + b) * 32 + lane];
+    }
+    const int motif = p.lane_motif[group * 32 + lane];
+    const int my_strand = DUAL ? 0 : p.lane_strand[group * 32 + lane];
+    const bool active = motif >= 0 && (DUAL || ((p.strands >> my_strand) & 1));
+    const int wm = motif >= 0 ? p.motif_width[motif] : 0;
+    const float thr_lo = active ? p.thr_lo[motif] : __int_as_float(0x7f800000);
+    const float thr_hi = active ? p.thr_hi[motif] : __int_as_float(0x7f800000);
+    const long long smax64 = row.g_len - row.g_off - (long long)wm;  // largest window start that fits (row-local)
+    const int smax = smax64 > 0x7fffffffLL ? 0x7fffffff : (smax64 < -1 ? -1 : (int)smax64);
+    const bool want_hits = p.hit_keys != nullptr;
+    const int key_shift = p.pos_bits + p.motif_bits;
+    const unsigned long long rowkey0 = (unsigned long long)(unsigned)p.out_rows[ch.row * 2 + 0] << key_shift;
+    const unsigned long long rowkey1 = (unsigned long long)(unsigned)p.out_rows[ch.row * 2 + 1] << key_shift;
+
+    const int c0 = ch.start;
+    const int c1 = min(c0 + p.chunk_len, row.n_own);  // owned window starts [c0, c1)
+    const int n_steps = (c1 - c0) + WB - 1;
+    const int n_words = (n_steps + 15) >> 4;
+    const uint32_t* __restrict__ wp = p.packed + row.word_off + (c0 >> 4);
+    const uint16_t* __restrict__ ap = p.amask + row.word_off + (c0 >> 4);
+    const uint8_t* __restrict__ cp = p.codes ? p.codes + row.word_off * 16 : nullptr;
+
+    V r[WB - 1];
+#pragma unroll
+    for (int k = 0; k < WB - 1; ++k) r[k] = V{};
+    int cnt0 = 0, cnt1 = 0;  // definite hits of this lane on strand 0 / 1
+    int nst = 0;             // staged hits (warp-uniform)
+
+    auto flush = [&]() {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&p.counters[SMG_CTR_HITS_APPENDED], (unsigned long long)nst);
+        base = __shfl_sync(SMG_FULL_MASK, base, 0);
+        for (int i = lane; i < nst; i += 32) {
+            if (base + i < p.hit_cap) {
+                p.hit_keys[base + i] = s_keys[i];
+                p.hit_scores[base + i] = s_scores[i];
+            }
+        }
+        nst = 0;
+        __syncwarp();
+    };
+
+    // one completed window score `v` of strand `st` for window start `s` (warp-uniform s)
+    auto emit = [&](const float v, const int s, const int st) {
+        const bool in_range = (s >= c0) & (s < c1);
+        const bool cand = in_range && (v > thr_lo) && (s <= smax) && (DUAL ? ((p.strands >> st) & 1) : true);
+        const unsigned cm = __ballot_sync(SMG_FULL_MASK, cand);
+        if (cm == 0) return;
+        const bool hit = cand && (v > thr_hi);
+        if (hit) {
+            if (st) ++cnt1; else ++cnt0;
+        }
+        if (cand && !hit) {  // near-threshold band: defer to the fp64 adjudicator
+            const unsigned long long i = atomicAdd(&p.counters[SMG_CTR_NEAR], 1ull);
+            if (i < p.near_cap) {
+                smg_near_t n;
+                n.row = ch.row; n.motif = motif; n.strand = st; n.start = s; n.score = v; n.reserved = 0;
+                p.near[i] = n;
+            }
+        }
+        if (want_hits) {
+            const unsigned hm = __ballot_sync(SMG_FULL_MASK, hit);
+            if (hm) {
+                if (hit) {
+                    const long long pos = st ? (smax64 - (long long)s) : (row.g_off + (long long)s);
+                    const int slot = nst + __popc(hm & lt_mask);
+                    s_keys[slot] = (st ? rowkey1 : rowkey0) | ((unsigned long long)pos << p.motif_bits) |
+                                   (unsigned long long)(unsigned)motif;
+                    s_scores[slot] = v;
+                }
+                nst += __popc(hm);
+                __syncwarp();
+                if (nst > kStageFlush) flush();
+            }
+        }
+    };
+    auto emit_v = [&](const V o, const int s) {
+        if (DUAL) {
+            emit(vget(o, 0), s, 0);
+            emit(vget(o, 1), s, 1);
+        } else {
+            emit(vget(o, 0), s, my_strand);
+        }
+    };
+
+    uint32_t w = wp[0];
+    uint32_t am = ap[0];
+    int s_base = c0 - (WB - 1);  // window start completed by the first step of the current word
+    for (int wi = 0; wi < n_words; ++wi) {
+        const uint32_t wn = wp[wi + 1];  // rows are padded, the prefetch never leaves the allocation
+        const uint32_t an = ap[wi + 1];
+        if (am == 0) {
+            // ---- ACGT fast path: 16 bases, threshold check every kU steps
+#pragma unroll 1
+            for (int blk = 0; blk < 16 / kU; ++blk) {
+                V o[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const uint32_t b = (w >> (2 * u)) & 3u;
+                    SMG_SWITCH_STEP(b, o[u]);
+                }
+                w >>= 2 * kU;
+                float m = vmax(o[0]);
+#pragma unroll
+                for (int u = 1; u < kU; ++u) m = vmax3(m, o[u]);
+                if (__any_sync(SMG_FULL_MASK, m > thr_lo)) {
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) emit_v(o[u], s_base + blk * kU + u);
+                }
+            }
+        } else {
+            // ---- generic path: IUPAC ambiguity codes, 'Z', and the padding past the end of the row
+#pragma unroll 1
+            for (int j = 0; j < 16; ++j) {
+                V o;
+                if (((am >> j) & 1u) == 0) {
+                    const uint32_t b = (w >> (2 * j)) & 3u;
+                    SMG_SWITCH_STEP(b, o);
+                } else {
+                    const int q = s_base + (WB - 1) + j;  // row-local position of this base
+                    const int code = (cp != nullptr && q < row.n_avail) ? (int)cp[q] : 0;
+                    const float e0 = c_emb[code][0], e1 = c_emb[code][1], e2 = c_emb[code][2], e3 = c_emb[code][3];
+                    o = vadd(r[WB - 2], vmix(e0, e1, e2, e3, t[WB - 1][0], t[WB - 1][1], t[WB - 1][2], t[WB - 1][3]));
+#pragma unroll
+                    for (int k = WB - 2; k >= 1; --k)
+                        r[k] = vadd(r[k - 1], vmix(e0, e1, e2, e3, t[k][0], t[k][1], t[k][2], t[k][3]));
+                    r[0] = vmix(e0, e1, e2, e3, t[0][0], t[0][1], t[0][2], t[0][3]);
+                }
+                if (__any_sync(SMG_FULL_MASK, vmax(o) > thr_lo)) emit_v(o, s_base + j);
+            }
+        }
+        w = wn;
+        am = an;
+        s_base += 16;
+    }
+
+    if (want_hits && nst > 0) flush();
+    if (p.counts != nullptr && motif >= 0) {
+        int32_t* c = p.counts + ((size_t)ch.row * p.n_motifs + motif) * 2;
+        if (cnt0) atomicAdd(c + 0, cnt0);
+        if (cnt1) atomicAdd(c + 1, cnt1);
+    }
+    int tot = cnt0 + cnt1;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) tot += __shfl_xor_sync(SMG_FULL_MASK, tot, d);
+    if (lane == 0 && tot) atomicAdd(&p.counters[SMG_CTR_DEFINITE], (unsigned long long)tot);
+}
+
+template <int WB, bool DUAL>
+void launch_scan_regtab(const ScanParams& p, int n_chunks, int n_groups, cudaStream_t stream)
+{
+    dim3 grid((unsigned)n_chunks, (unsigned)n_groups, 1);
+    scan_regtab_kernel<WB, DUAL><<<grid, 32, 0, stream>>>(p);
+}
+
+}  // namespace smg

@@ -1,0 +1,321 @@
+"""Device-side objects of the scan path: packed sequence batches, PWM tables and the fused scan driver.
+
+Everything here talks to libsmeagol_b200.so through the C-ABI (smeagol_b200._lib); torch is used only for device
+memory, streams and (in dist.py) torch.distributed.  There is no CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+ROW_DTYPE = np.dtype(_lib.ROW_DTYPE_FIELDS)
+CHUNK_DTYPE = np.dtype([("row", "<i4"), ("start", "<i4")])
+NEAR_DTYPE = np.dtype([("row", "<i4"), ("motif", "<i4"), ("strand", "<i4"), ("start", "<i4"), ("score", "<f4"),
+                       ("reserved", "<i4")])
+ROW_PAD_BASES = 96  # every row is followed by at least this many 'Z' bases (halo + one prefetched word)
+NEAR_REL = 1e-5     # half-width of the near-threshold band, relative to sum_k max_b |T[k,b]|
+STRANDS = {"none": 1, "only": 2, "both": 3}
+
+
+def _require_cuda(device=None):
+    if not torch.cuda.is_available():
+        raise _lib.SmeagolB200Error("smeagol_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _to_dev(arr, device):
+    """numpy (any dtype / structured) -> device uint8 tensor holding the same bytes."""
+    raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+    return torch.from_numpy(raw).to(device, non_blocking=False)
+
+
+def _as_bytes(seq):
+    if isinstance(seq, (bytes, bytearray, memoryview)):
+        return np.frombuffer(seq, dtype=np.uint8)
+    if isinstance(seq, np.ndarray):
+        return np.ascontiguousarray(seq, dtype=np.uint8).reshape(-1)
+    return np.frombuffer(str(seq).encode("latin-1"), dtype=np.uint8)
+
+
+class SeqBatch:
+    """Rows packed on the GPU at 2 bits/base + 1-bit ambiguity mask (+ uint8 codes only if ambiguity exists).
+
+    Replaces encode.integer_encode / SeqEncoding's (N, L) float32 array (smeagol/encode.py:47-68, 109-160).
+    seqs: list of str / bytes / uint8 arrays (ASCII, or integer codes 0..16 when kind='codes').
+    segments: optional list of (g_off, g_len, n_own) per row for rows that are segments of a longer sequence
+    (chunked or multi-GPU scans); n_avail is the row's length (owned part + right halo).
+    """
+
+    def __init__(self, seqs, kind="ascii", segments=None, device=None, pinned=True):
+        self.device = _require_cuda(device)
+        lib = _lib.load()
+        arrs = [_as_bytes(s) for s in seqs]
+        n_rows = len(arrs)
+        if n_rows == 0:
+            raise ValueError("SeqBatch needs at least one row")
+        lens = np.array([a.shape[0] for a in arrs], dtype=np.int64)
+        if lens.max() >= 2 ** 31 - 256:
+            raise ValueError("rows longer than 2^31 bases must be split into segments")
+        rows = np.zeros(n_rows, dtype=ROW_DTYPE)
+        row_words = ((lens + ROW_PAD_BASES + 63) // 64) * 4
+        rows["word_off"] = np.concatenate([[0], np.cumsum(row_words)[:-1]])
+        rows["n_avail"] = lens
+        if segments is None:
+            rows["g_off"] = 0
+            rows["g_len"] = lens
+            rows["n_own"] = lens
+        else:
+            seg = np.asarray(segments, dtype=np.int64).reshape(n_rows, 3)
+            rows["g_off"], rows["g_len"], rows["n_own"] = seg[:, 0], seg[:, 1], seg[:, 2]
+        self.total_words = int(row_words.sum())
+        src_off = np.concatenate([[0], np.cumsum((lens + 15) // 16 * 16)[:-1]]).astype(np.int64)
+        total_src = int(src_off[-1] + (lens[-1] + 15) // 16 * 16)
+        host = torch.empty(max(total_src, 16), dtype=torch.uint8, pin_memory=pinned)
+        hnp = host.numpy()
+        for a, o in zip(arrs, src_off):
+            hnp[o:o + a.shape[0]] = a
+        self.h2d_bytes = int(total_src)
+        d_src = host.to(self.device, non_blocking=True)
+        self.rows_host = rows
+        self.n_rows = n_rows
+        self.lens = lens
+        self.d_rows = _to_dev(rows, self.device)
+        d_src_off = torch.from_numpy(src_off).to(self.device)
+        self.packed = torch.empty(self.total_words, dtype=torch.int32, device=self.device)
+        self.amask = torch.empty(self.total_words, dtype=torch.int16, device=self.device)
+        codes = torch.empty(self.total_words * 16, dtype=torch.uint8, device=self.device)
+        status = torch.tensor([-1, 0], dtype=torch.int64, device=self.device)
+        _lib.check(lib.smg_pack(_ptr(d_src), 0 if kind == "ascii" else 1, _ptr(self.d_rows), _ptr(d_src_off), n_rows,
+                                self.total_words, _ptr(self.packed), _ptr(self.amask), _ptr(codes), _ptr(status), _stream()),
+                   "smg_pack")
+        st = status.cpu().numpy()
+        if st[0] >= 0:
+            r = int(np.searchsorted(src_off, st[0], side="right") - 1)
+            bad = arrs[r][int(st[0] - src_off[r])]
+            raise KeyError(chr(int(bad)) if kind == "ascii" else int(bad))
+        self.has_ambiguity = bool(st[1])
+        self.codes = codes if self.has_ambiguity else None
+        self.total_own = int(rows["n_own"].clip(min=0).sum())
+        self.max_g_len = int(rows["g_len"].max())
+
+    def chunks(self, chunk_len):
+        """Work list of (row, first owned start) pairs, chunk_len a multiple of 16."""
+        n_own = self.rows_host["n_own"].astype(np.int64).clip(min=0)
+        per_row = (n_own + chunk_len - 1) // chunk_len
+        total = int(per_row.sum())
+        ch = np.zeros(total, dtype=CHUNK_DTYPE)
+        if total:
+            ch["row"] = np.repeat(np.arange(self.n_rows, dtype=np.int32), per_row)
+            first = np.repeat(np.cumsum(per_row) - per_row, per_row)
+            ch["start"] = ((np.arange(total, dtype=np.int64) - first) * chunk_len).astype(np.int32)
+        return ch
+
+
+class DevicePWMSet:
+    """Device tables of a PWM library (models.py:70-90 pads PWMs into one Conv1D kernel; here: natural fp32 tables,
+    reverse-complement tables and lane-major register-table groups, built by smg_pwmset_create)."""
+
+    def __init__(self, weights, device=None):
+        self.device = _require_cuda(device)
+        lib = _lib.load()
+        w32 = [np.ascontiguousarray(np.asarray(w), dtype=np.float32) for w in weights]
+        for w in w32:
+            if w.ndim != 2 or w.shape[1] != 4:
+                raise ValueError("PWM weights must have shape (W, 4)")
+            if not np.all(np.isfinite(w)):
+                raise ValueError("PWM weights must be finite (the reference's conv yields NaN for -inf entries)")
+        self.n_motifs = len(w32)
+        self.widths = np.array([w.shape[0] for w in w32], dtype=np.int32)
+        flat = np.concatenate([w.reshape(-1) for w in w32]).astype(np.float32)
+        self.abs_scale = np.array([np.abs(w.astype(np.float64)).max(axis=1).sum() for w in w32])
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.smg_pwmset_create(flat.ctypes.data_as(ctypes.c_void_p), self.widths.ctypes.data_as(ctypes.c_void_p),
+                                             self.n_motifs, ctypes.byref(handle)), "smg_pwmset_create")
+        self.handle = handle
+        info = (ctypes.c_int64 * 8)()
+        _lib.check(lib.smg_pwmset_info(handle, info), "smg_pwmset_info")
+        self.max_width = int(info[1])
+        self.n_groups = int(info[2])
+        self.n_buckets = int(info[3])
+        self.n_wide = int(info[4])
+        self.sum_padded_width = int(info[5])
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.load().smg_pwmset_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _round_down_f32(x):
+    f = x.astype(np.float32)
+    up = f.astype(np.float64) > x
+    f[up] = np.nextafter(f[up], np.float32(-np.inf))
+    return f
+
+
+def _round_up_f32(x):
+    f = x.astype(np.float32)
+    dn = f.astype(np.float64) < x
+    f[dn] = np.nextafter(f[dn], np.float32(np.inf))
+    return f
+
+
+def threshold_bounds(thr64, abs_scale, adjudicate=True):
+    """fp32 kernel bounds for `score > thr`: with adjudication a band of NEAR_REL * abs_scale around thr goes to the
+    fp64 adjudicator; without it thr_lo == thr_hi == largest float <= thr reproduces `(double)score_f32 > thr`
+    (models.py:108) exactly."""
+    thr64 = np.asarray(thr64, dtype=np.float64)
+    if adjudicate:
+        band = NEAR_REL * np.asarray(abs_scale, dtype=np.float64)
+        return _round_down_f32(thr64 - band), _round_up_f32(thr64 + band)
+    lo = _round_down_f32(thr64)
+    return lo, lo.copy()
+
+
+def _bits(n):
+    return max(1, int(n - 1).bit_length()) if n > 1 else 1
+
+
+class ScanResult:
+    """Sorted hits (device), count table (device) and bookkeeping of one fused scan."""
+
+    def __init__(self, keys, scores, n_hits, counts, pos_bits, motif_bits, stats):
+        self.keys, self.scores, self.n_hits, self.counts = keys, scores, n_hits, counts
+        self.pos_bits, self.motif_bits, self.stats = pos_bits, motif_bits, stats
+
+    def hits_host(self):
+        """(out_row, pos, motif) int64 arrays + float32 scores, in (row, pos, motif) order."""
+        if self.keys is None or self.n_hits == 0:
+            z = np.zeros(0, dtype=np.int64)
+            return z, z.copy(), z.copy(), np.zeros(0, dtype=np.float32)
+        k = self.keys[:self.n_hits].cpu().numpy().view(np.uint64)
+        sc = self.scores[:self.n_hits].cpu().numpy()
+        motif = (k & np.uint64((1 << self.motif_bits) - 1)).astype(np.int64)
+        pos = ((k >> np.uint64(self.motif_bits)) & np.uint64((1 << self.pos_bits) - 1)).astype(np.int64)
+        row = (k >> np.uint64(self.motif_bits + self.pos_bits)).astype(np.int64)
+        return row, pos, motif, sc
+
+    def key_checksum(self):
+        """Order-independent checksum of the hit set (sum and xor of the keys), computed on the device."""
+        if self.keys is None or self.n_hits == 0:
+            return 0, 0
+        k = self.keys[:self.n_hits]
+        x = k.clone()
+        while x.numel() > 1:  # xor-reduce
+            h = x.numel() // 2
+            y = torch.bitwise_xor(x[:h], x[h:2 * h])
+            x = torch.cat([y, x[2 * h:]]) if x.numel() % 2 else y
+        return int(k.sum().item()), int(x.item())
+
+
+def pick_chunk_len(total_own, n_groups, target_ctas=148 * 16 * 8):
+    c = (total_own * max(n_groups, 1)) // max(target_ctas, 1)
+    c = ((c + 15) // 16) * 16
+    return int(min(4096, max(256, c)))
+
+
+def scan(pwmset, batch, thr64, strands, out_rows, n_out_rows, want_hits=True, want_counts=True, adjudicate=True,
+         chunk_len=None, hit_cap=None, near_cap=None, sort=True, workspace=None):
+    """Fused two-strand scan of a SeqBatch against a DevicePWMSet.
+
+    thr64: per-PWM thresholds (frac * max_scores, computed by the caller exactly as models.py:141 does).
+    out_rows: int32 (n_rows, 2) output row of (row, strand) in the reference's row order; n_out_rows their count.
+    Returns a ScanResult.  Hit-buffer overflow is detected and the scan retried with a larger buffer, never truncated.
+    """
+    lib = _lib.load()
+    dev = batch.device
+    M = pwmset.n_motifs
+    thr64 = np.ascontiguousarray(thr64, dtype=np.float64)
+    assert thr64.shape == (M,)
+    lo, hi = threshold_bounds(thr64, pwmset.abs_scale, adjudicate)
+    motif_bits = _bits(M)
+    pos_bits = _bits(batch.max_g_len + 1)
+    row_bits = _bits(n_out_rows)
+    if motif_bits + pos_bits + row_bits > 63:
+        raise ValueError("hit key does not fit in 63 bits (rows=%d, length=%d, motifs=%d)" % (n_out_rows, batch.max_g_len, M))
+    if chunk_len is None:
+        chunk_len = pick_chunk_len(batch.total_own, pwmset.n_groups)
+    chunks = batch.chunks(chunk_len)
+    d_chunks = _to_dev(chunks, dev) if len(chunks) else torch.zeros(8, dtype=torch.uint8, device=dev)
+    d_lo = torch.from_numpy(lo).to(dev)
+    d_hi = torch.from_numpy(hi).to(dev)
+    d_thr = torch.from_numpy(thr64).to(dev)
+    d_out_rows = torch.from_numpy(np.ascontiguousarray(out_rows, dtype=np.int32)).to(dev)
+    n_strands = bin(strands).count("1")
+    cells = batch.total_own * M * n_strands
+    if hit_cap is None:
+        hit_cap = int(min(max(1 << 16, cells * 0.004), 1 << 31))
+    if near_cap is None:
+        near_cap = 1 << 16
+    counts = torch.zeros((batch.n_rows, M, 2), dtype=torch.int32, device=dev) if want_counts else None
+    while True:
+        counters = torch.zeros(_lib.N_COUNTERS, dtype=torch.int64, device=dev)
+        keys = torch.empty(hit_cap, dtype=torch.int64, device=dev) if want_hits else None
+        scores = torch.empty(hit_cap, dtype=torch.float32, device=dev) if want_hits else None
+        near = torch.empty(near_cap * _lib.NEAR_BYTES, dtype=torch.uint8, device=dev)
+        if counts is not None:
+            counts.zero_()
+        _lib.check(lib.smg_scan(pwmset.handle, _ptr(batch.packed), _ptr(batch.amask), _ptr(batch.codes), _ptr(batch.d_rows),
+                                batch.n_rows, _ptr(d_out_rows), _ptr(d_chunks), len(chunks), chunk_len, strands, _ptr(d_lo),
+                                _ptr(d_hi), pos_bits, motif_bits, _ptr(keys), _ptr(scores), hit_cap, _ptr(near), near_cap,
+                                _ptr(counts), _ptr(counters), _stream()), "smg_scan")
+        if adjudicate:
+            _lib.check(lib.smg_adjudicate(pwmset.handle, _ptr(batch.packed), _ptr(batch.amask), _ptr(batch.codes),
+                                          _ptr(batch.d_rows), _ptr(d_out_rows), _ptr(d_thr), _ptr(near), near_cap, pos_bits,
+                                          motif_bits, _ptr(keys), _ptr(scores), hit_cap, _ptr(counts), _ptr(counters),
+                                          _stream()), "smg_adjudicate")
+        c = counters.cpu().numpy()
+        n_app, n_near = int(c[_lib.CTR_HITS_APPENDED]), int(c[_lib.CTR_NEAR])
+        if n_near > near_cap:
+            near_cap = int(n_near * 1.25) + 1024
+            continue
+        if want_hits and n_app > hit_cap:
+            hit_cap = int(n_app * 1.1) + 1024
+            continue
+        break
+    n_hits = n_app if want_hits else 0
+    stats = {"n_definite": int(c[_lib.CTR_DEFINITE]), "n_near": n_near, "n_adjudicated_accepted": int(c[_lib.CTR_ADJ_ACCEPTED]),
+             "n_hits_total": int(c[_lib.CTR_DEFINITE]) + int(c[_lib.CTR_ADJ_ACCEPTED]), "chunk_len": chunk_len,
+             "n_chunks": len(chunks), "hit_cap": hit_cap, "near_cap": near_cap}
+    if want_hits and sort and n_hits > 0:
+        keys, scores = sort_hits(keys, scores, n_hits, motif_bits + pos_bits + row_bits)
+    return ScanResult(keys, scores, n_hits, counts, pos_bits, motif_bits, stats)
+
+
+def sort_hits(keys, scores, n, key_bits):
+    lib = _lib.load()
+    dev = keys.device
+    keys_out = torch.empty(n, dtype=torch.int64, device=dev)
+    scores_out = torch.empty(n, dtype=torch.float32, device=dev)
+    tb = ctypes.c_uint64(0)
+    _lib.check(lib.smg_sort_hits(_ptr(keys), _ptr(scores), _ptr(keys_out), _ptr(scores_out), n, key_bits, None,
+                                 ctypes.byref(tb), _stream()), "smg_sort_hits(query)")
+    temp = torch.empty(max(int(tb.value), 16), dtype=torch.uint8, device=dev)
+    _lib.check(lib.smg_sort_hits(_ptr(keys), _ptr(scores), _ptr(keys_out), _ptr(scores_out), n, key_bits, _ptr(temp),
+                                 ctypes.byref(tb), _stream()), "smg_sort_hits")
+    return keys_out, scores_out
+
+
+def predict_dense(pwmset, batch, row_len):
+    lib = _lib.load()
+    out = torch.empty((batch.n_rows, row_len, pwmset.n_motifs), dtype=torch.float32, device=batch.device)
+    _lib.check(lib.smg_predict_dense(pwmset.handle, _ptr(batch.packed), _ptr(batch.amask), _ptr(batch.codes), _ptr(batch.d_rows),
+                                     batch.n_rows, row_len, _ptr(out), _stream()), "smg_predict_dense")
+    return out

@@ -1,0 +1,348 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C-ABI, against the CPU
+oracle on the same seeded inputs and against the committed golden fixtures of the reference.
+
+Bars: hit sets / positions / counts identical (bit-exact integer work); fp32 scores BIT-EXACT against the oracle's
+kernel-order fp32 leg and within 1e-5 relative (SCORE_RTOL, north_star) of the reference-order leg and of the fp64
+leg; sites inside the 1e-5 near-threshold band are decided in fp64 on both sides.
+"""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from golden_util import (SCORE_RTOL, assert_frame_matches, case_kwargs, fix_stats_ddof, golden, pwm_df,
+                         pwms_from_json)
+from oracle import frames as of
+from oracle import scan_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def _sb():
+    import smeagol_b200
+
+    return smeagol_b200
+
+
+def synth_pwms(rng, n, wmin, wmax, dtype=np.float64):
+    ws = []
+    for _ in range(n):
+        W = int(rng.integers(wmin, wmax + 1))
+        ppm = (rng.dirichlet([0.5] * 4, size=W) + 0.01) / 1.04
+        ws.append(np.log2(ppm / 0.25).astype(dtype))
+    return pd.DataFrame({"Matrix_id": ["M%04d" % i for i in range(n)], "weights": ws})
+
+
+def rand_seq(rng, L, alphabet="ACGT", p=None):
+    return "".join(rng.choice(list(alphabet), size=L, p=p))
+
+
+def device_scan(model, seqs, frac, rcomp="both", chunk_len=None, segments=None, adjudicate=True):
+    """Scan forward strings as ONE group -> (row, pos, motif, score) with rows [fwd..., rc...] like the oracle."""
+    from smeagol_b200 import device as dev
+
+    n = len(seqs)
+    batch = dev.SeqBatch(seqs, segments=segments)
+    if rcomp == "none":
+        out_rows = np.stack([np.arange(n), np.zeros(n)], axis=1)
+    elif rcomp == "only":
+        out_rows = np.stack([np.zeros(n), np.arange(n)], axis=1)
+    else:
+        out_rows = np.stack([np.arange(n), n + np.arange(n)], axis=1)
+    res = dev.scan(model.device_set, batch, model.thresholds(frac), dev.STRANDS[rcomp], out_rows.astype(np.int32),
+                   2 * n if rcomp == "both" else n, adjudicate=adjudicate, chunk_len=chunk_len)
+    return res
+
+
+def check_against_oracle(model, seqs, frac, rcomp="both", chunk_len=None, atol=0.0):
+    """atol: only for thresholds near 0, where hits have scores near 0 and a relative bound is meaningless for any
+    fp32 sum; 1e-5 absolute is 1e-5 relative to the PWM score scale there."""
+    res = device_scan(model, seqs, frac, rcomp, chunk_len)
+    row, pos, motif, sc = res.hits_host()
+    exp = so.scan_rows(seqs, model.weights, frac, rcomp=rcomp, order="kernel", adjudicate=True)
+    np.testing.assert_array_equal(row, exp["row"])
+    np.testing.assert_array_equal(pos, exp["pos"])
+    np.testing.assert_array_equal(motif, exp["motif"])
+    # fp32 scores: bit-exact against the same summation order
+    np.testing.assert_array_equal(sc.view(np.uint32), exp["score"].view(np.uint32))
+    np.testing.assert_allclose(sc, exp["score64"], rtol=SCORE_RTOL, atol=atol)
+    ref = so.scan_rows(seqs, model.weights, frac, rcomp=rcomp, order="ref", adjudicate=True)
+    np.testing.assert_array_equal(pos, ref["pos"])
+    np.testing.assert_allclose(sc, ref["score"], rtol=SCORE_RTOL, atol=atol)
+    # count table (device) == counts of the hit list
+    n_rows = len(exp["rows"])
+    ct = so.count_table(exp, n_rows, len(model.weights))
+    dev_counts = res.counts.cpu().numpy()
+    n = len(seqs)
+    if rcomp == "both":
+        got = np.concatenate([dev_counts[:, :, 0], dev_counts[:, :, 1]], axis=0)
+    elif rcomp == "none":
+        got = dev_counts[:, :, 0]
+    else:
+        got = dev_counts[:, :, 1]
+    np.testing.assert_array_equal(got, ct)
+    assert res.stats["n_hits_total"] == len(exp["row"])
+    return res, exp
+
+
+def test_models_kat():
+    """tests/test_models.py:30-74 of the reference, through the device path."""
+    sb = _sb()
+    G = golden()
+    model = sb.models.PWMModel(pwm_df(G["test_pwms"]))
+    assert np.all(model.Matrix_ids == ["x", "y", "z"])
+    assert np.all(model.widths == [3, 5, 3])
+    assert sb.utils._equals(model.max_scores, np.array([3.33376361, 5.52770673, 2.50816981]))
+    assert model.channels == 3 and model.max_width == 5
+    preds = model.predict(np.array([[1, 2, 3]]))
+    assert preds.shape == (1, 3, 3)
+    assert sb.utils._equals(preds[0, 0, :], np.array([-1.60847875, -7.32647115, 0.35611725000000005]))
+    np.testing.assert_allclose(preds, np.array(G["test_models"]["predict_out"]), rtol=1e-6, atol=1e-6)
+    (r, p, m), sc = model.predict_with_threshold(np.array([[1, 2, 3]]), 0.1, score=True)
+    assert list(r) == [0] and list(p) == [0] and list(m) == [2]
+    assert sb.utils._equals(sc, np.array([0.35611725]))
+    with pytest.raises(AssertionError):
+        model.predict_with_threshold(np.array([[1, 2, 3]]), 1.5)
+
+
+def test_predict_dense_iupac():
+    sb = _sb()
+    P = golden()["predict_iupac"]
+    model = sb.models.PWMModel(pwm_df(P["pwms"]))
+    codes = sb.encode.integer_encode(P["seq"])
+    got = model.predict(codes[None, :])
+    np.testing.assert_allclose(got, np.array(P["out"]), rtol=1e-5, atol=2e-6)
+    exp = so.predict(codes[None, :].astype(np.uint8), model.weights)
+    np.testing.assert_array_equal(got.view(np.uint32), exp.view(np.uint32))  # same order -> bit-exact
+
+
+def test_encode_errors_and_pack():
+    sb = _sb()
+    from smeagol_b200 import device as dev
+
+    with pytest.raises(KeyError):
+        dev.SeqBatch(["ACGTACGTACGTACGTAE"])
+    with pytest.raises(KeyError):
+        dev.SeqBatch(["acgt"])  # the reference's alphabet is upper-case only
+    b = dev.SeqBatch(["ACGTUNZ", "WSMKRYBDHV" * 3])
+    assert b.has_ambiguity
+    packed = b.packed.cpu().numpy().view(np.uint32)
+    amask = b.amask.cpu().numpy().view(np.uint16)
+    codes = b.codes.cpu().numpy()
+    assert packed[0] & 0x3FF == (0 | 1 << 2 | 2 << 4 | 3 << 6 | 3 << 8)
+    assert amask[0] == 0xFFFF & ~0x1F
+    assert list(codes[:7]) == [1, 2, 3, 4, 5, 6, 0]
+    w1 = int(b.rows_host["word_off"][1])
+    assert list(codes[w1 * 16:w1 * 16 + 10]) == [7, 8, 9, 10, 11, 12, 13, 14, 15, 16]
+    assert not dev.SeqBatch(["ACGTU" * 10]).has_ambiguity
+
+
+@pytest.mark.parametrize("i", range(13))
+def test_reference_scan_cases(i):
+    """scan_sequences of this framework vs the reference's recorded outputs and vs the adjudicated oracle."""
+    sb = _sb()
+    case = golden()["scan_cases"][i]
+    model = sb.models.PWMModel(pwm_df(case["pwms"]))
+    thr, kw = case_kwargs(case)
+    recs = [sb.SeqRecord(sb.Seq(s), id=i_, name=n_) for s, i_, n_ in zip(case["seqs"], case["ids"], case["names"])]
+    out = sb.scan.scan_sequences(recs, model, thr, **kw)
+    ids, ws = pwms_from_json(case["pwms"])
+    exp = of.scan_sequences(case["seqs"], case["ids"], case["names"], ids, ws, thr, order="ref", adjudicate=True, **kw)
+    exp.pop("_n_flipped")
+    assert set(out.keys()) == set(exp.keys())
+    for k in exp:
+        assert_frame_matches(out[k], exp[k], case["name"] + ":" + k)
+    # against the reference's own recorded output: identical unless a site sits in the near-threshold band
+    pure = of.scan_sequences(case["seqs"], case["ids"], case["names"], ids, ws, thr, order="ref", adjudicate=False, **kw)
+    if pure.pop("_n_flipped") == 0:
+        for k, e in case["outputs"].items():
+            assert_frame_matches(out[k], fix_stats_ddof(k, e), case["name"] + ":golden:" + k)
+    else:
+        assert case["name"] == "no_hits"
+
+
+def test_enrich_golden(tmp_path):
+    """tests/test_enrich.py:28-69 of the reference end to end (sites, counts, background stats, p / fdr)."""
+    sb = _sb()
+    G = golden()
+    E = G["test_enrich"]
+    model = sb.models.PWMModel(pwm_df(G["test_pwms"]))
+    genome = [sb.SeqRecord(sb.Seq(s), id=i, name=i) for s, i in zip(E["genome"], E["ids"])]
+    fa = os.path.join(str(tmp_path), "shuf_genome.fa.gz")
+    sb.io.write_fasta([sb.SeqRecord(sb.Seq(s), id=i, name=i, description="") for i, s in E["shuf_genome"]], fa)
+    res = sb.enrich.enrich_in_genome(genome, model, simN=10, simK=2, rcomp="both", sense="+", threshold=0.65,
+                                     background="binomial", shuf_seqs=fa)
+    csv = E["csv"]
+    sites = res["real_sites"]
+    assert np.all(sites.start == np.array(csv["real_sites"]["start"]) - 1)
+    assert np.all(sites.sense == csv["real_sites"]["sense"])
+    assert list(sites.Matrix_id) == csv["real_sites"]["m"]
+    counts = res["real_counts"]
+    assert list(counts.Matrix_id) == csv["real_counts"]["Matrix_id"]
+    assert list(counts.sense) == csv["real_counts"]["sense"]
+    assert list(counts.num) == csv["real_counts"]["num"]
+    st = res["shuf_stats"]
+    assert list(st.Matrix_id) == csv["shuf_stats"]["Matrix_id"]
+    assert list(st.sense) == csv["shuf_stats"]["sense"]
+    assert np.all(st.avg == csv["shuf_stats"]["avg"])
+    assert all(sb.utils._equals(a, b) for a, b in zip(st.sd, csv["shuf_stats"]["sd"]))
+    enr = res["enrichment"]
+    assert list(enr.Matrix_id) == csv["enr"]["Matrix_id"]
+    assert list(enr.sense) == csv["enr"]["sense"]
+    assert all(sb.utils._equals(a, b) for a, b in zip(enr.p, csv["enr"]["p"]))
+    assert all(sb.utils._equals(a, b) for a, b in zip(enr.fdr, csv["enr"]["fdr"]))
+    assert list(enr.adj_len) == csv["enr"]["adj_len"]
+
+
+def test_all_width_buckets_bit_exact():
+    """Every register-table instantiation (padded widths 2..32, dual and single strand) plus the wide fallback."""
+    sb = _sb()
+    rng = np.random.default_rng(7)
+    ws = []
+    for W in list(range(1, 41)) * 2:  # widths 1..40, two of each -> partial warps in every bucket
+        ppm = (rng.dirichlet([0.5] * 4, size=W) + 0.01) / 1.04
+        ws.append(np.log2(ppm / 0.25))
+    model = sb.models.PWMModel(pd.DataFrame({"Matrix_id": ["W%02d_%d" % (w.shape[0], i) for i, w in enumerate(ws)],
+                                             "weights": ws}))
+    seqs = [rand_seq(rng, 1500), rand_seq(rng, 700), rand_seq(rng, 31), rand_seq(rng, 5)]
+    check_against_oracle(model, seqs, 0.55, "both", chunk_len=256)
+    check_against_oracle(model, seqs, 0.55, "none", chunk_len=4096)
+    check_against_oracle(model, seqs, 0.55, "only", chunk_len=256)
+
+
+def test_many_motifs_random_and_iupac():
+    sb = _sb()
+    rng = np.random.default_rng(11)
+    model = sb.models.PWMModel(synth_pwms(rng, 150, 5, 24))
+    amb = "ACGTNWSMKRYBDHVZ"  # (U together with T is "Mixed RNA/DNA" for Biopython's reverse_complement)
+    pa = np.array([0.23] * 4 + [0.08 / 12] * 12)
+    seqs = [rand_seq(rng, 3000), rand_seq(rng, 2111, amb, pa / pa.sum()), "N" * 300 + rand_seq(rng, 500) + "N" * 100]
+    res, exp = check_against_oracle(model, seqs, 0.6, "both", chunk_len=512)
+    assert len(exp["row"]) > 500
+
+
+def test_thresholds_low_and_float32_weights():
+    sb = _sb()
+    rng = np.random.default_rng(13)
+    model = sb.models.PWMModel(synth_pwms(rng, 40, 6, 12, dtype=np.float32))
+    seqs = [rand_seq(rng, 800)]
+    check_against_oracle(model, seqs, 0.3, "both", atol=1e-5)  # dense hits: staging flushes and buffer growth
+    check_against_oracle(model, seqs, 0.0, "both", atol=1e-5)
+    check_against_oracle(model, seqs, 1.0, "both")   # thr == max score: near-threshold band, fp64 adjudication
+
+
+def test_pure_reference_compare_mode():
+    """adjudicate=False reproduces `(double)score_f32 > thr` (models.py:108) on the kernel-order fp32 scores."""
+    sb = _sb()
+    rng = np.random.default_rng(17)
+    model = sb.models.PWMModel(synth_pwms(rng, 60, 7, 12), adjudicate=False)
+    seqs = [rand_seq(rng, 2000), rand_seq(rng, 999)]
+    res = device_scan(model, seqs, 0.55, "both", adjudicate=False)
+    row, pos, motif, sc = res.hits_host()
+    exp = so.scan_rows(seqs, model.weights, 0.55, rcomp="both", order="kernel", adjudicate=False)
+    np.testing.assert_array_equal(row, exp["row"])
+    np.testing.assert_array_equal(pos, exp["pos"])
+    np.testing.assert_array_equal(motif, exp["motif"])
+    np.testing.assert_array_equal(sc.view(np.uint32), exp["score"].view(np.uint32))
+
+
+def test_segments_halo_ownership_equals_whole():
+    """A long sequence scanned as segments with a W_max-1 right halo (window owned by the segment containing its
+    start) gives exactly the hit set of the whole sequence, on both strands."""
+    sb = _sb()
+    rng = np.random.default_rng(19)
+    model = sb.models.PWMModel(synth_pwms(rng, 70, 6, 24))
+    L = 10000
+    seq = rand_seq(rng, L)
+    whole = device_scan(model, [seq], 0.6, "both")
+    halo = int(model.max_width) - 1
+    bounds = [0, 1777, 4096, 4100, 9000, L]
+    parts, segs = [], []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        e = min(L, b + halo)
+        parts.append(seq[a:e])
+        segs.append((a, L, b - a))
+    from smeagol_b200 import device as dev
+
+    batch = dev.SeqBatch(parts, segments=segs)
+    n = len(parts)
+    out_rows = np.stack([np.zeros(n), np.ones(n)], axis=1).astype(np.int32)  # all segments -> output rows 0 (+) / 1 (-)
+    res = dev.scan(model.device_set, batch, model.thresholds(0.6), 3, out_rows, 2, chunk_len=256)
+    a = whole.hits_host()
+    b = res.hits_host()
+    for x, y in zip(a[:3], b[:3]):
+        np.testing.assert_array_equal(x, y)
+    np.testing.assert_array_equal(a[3].view(np.uint32), b[3].view(np.uint32))
+    np.testing.assert_array_equal(whole.counts.cpu().numpy().sum(axis=0), res.counts.cpu().numpy().sum(axis=0))
+    assert whole.key_checksum() == res.key_checksum()
+
+
+def test_size_independent_properties_large():
+    """Config-2-like size (1,000,000 bases x 200 PWMs): properties that need no oracle -- chunk-size invariance,
+    strand symmetry (scanning the reverse complement swaps the strands), counts == histogram of the hit list."""
+    sb = _sb()
+    rng = np.random.default_rng(23)
+    model = sb.models.PWMModel(synth_pwms(rng, 200, 7, 12))
+    L = 1_000_000
+    seq = "".join(np.array(list("ACGT"))[rng.integers(0, 4, size=L)])
+    a = device_scan(model, [seq], 0.7, "both", chunk_len=4096)
+    b = device_scan(model, [seq], 0.7, "both", chunk_len=1024)
+    assert a.n_hits == b.n_hits and a.key_checksum() == b.key_checksum()
+    row, pos, motif, sc = a.hits_host()
+    assert np.all(np.diff((row << 40) | (pos << 12) | motif) > 0)  # sorted, unique
+    cnt = a.counts.cpu().numpy()[0]
+    hist = np.zeros((200, 2), dtype=np.int64)
+    np.add.at(hist, (motif, row), 1)
+    np.testing.assert_array_equal(cnt, hist)
+    rc = so.reverse_complement_str(seq)
+    c = device_scan(model, [rc], 0.7, "both", chunk_len=4096)
+    row_c, pos_c, motif_c, sc_c = c.hits_host()
+    # '+' hits of rc(seq) at position p  <->  '-' hits of seq at position p (the reference scans the rc string)
+    np.testing.assert_array_equal(pos_c[row_c == 0], pos[row == 1])
+    np.testing.assert_array_equal(motif_c[row_c == 0], motif[row == 1])
+    np.testing.assert_allclose(sc_c[row_c == 0], sc[row == 1], rtol=SCORE_RTOL)
+    # a 1 Mb parity slice against the oracle is too slow in numpy for 200 PWMs; check the first 20 kb exactly
+    check_against_oracle(model, [seq[:20000]], 0.7, "both")
+
+
+def test_variant_golden_and_random():
+    """tests/test_variant.py:47-63 of the reference + random sites/variants recorded from the reference."""
+    sb = _sb()
+    G = golden()
+    V = G["test_variant"]
+    recs = [sb.SeqRecord(sb.Seq(s), id=i, name=i) for s, i in zip(V["seqs"], V["ids"])]
+    result = sb.variant.variant_effect_on_sites(pd.DataFrame(V["sites"]), pd.DataFrame(V["variants"]), recs,
+                                                pwm_df(G["test_pwms"]))
+    assert len(result) == 3
+    assert list(result["name"]) == ["seq0", "seq1", "seq1"] and list(result["pos"]) == [2, 0, 1]
+    assert list(result["alt"]) == ["G", "A", "A"] and list(result["Matrix_id"]) == ["x", "z", "z"]
+    assert list(result["seq"]) == ["GAC", "GCT", "GCT"]
+    assert sb.utils._equals(result.max_score.values, np.array([3.33376361, 2.50816981, 2.50816981]))
+    assert sb.utils._equals(result.score.values, np.array([1.0, 0.769149, 0.769149]))
+    assert sb.utils._equals(result.variant_score.values, np.array([0.4080668, 0.1419828, 0.769149]))
+    R = G["variant_random"]
+    recs = [sb.SeqRecord(sb.Seq(s), id=i, name=i) for s, i in zip(R["seqs"], R["ids"])]
+    got = sb.variant.variant_effect_on_sites(pd.DataFrame(R["sites"]), pd.DataFrame(R["variants"]), recs, pwm_df(R["pwms"]))
+    exp = R["result"]
+    assert len(got) == len(exp["pos"])
+    for c in ("name", "pos", "alt", "start", "Matrix_id", "end", "seq"):
+        assert list(got[c]) == list(exp[c]), c
+    # device tables are the fp32 casts of the fp64 weights: 1e-5 relative (absolute floor for scores near 0)
+    np.testing.assert_allclose(got["score"], exp["score"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(got["variant_score"], exp["variant_score"], rtol=1e-5, atol=1e-6)
+
+
+def test_variant_windows_batched():
+    """BASELINE config 5 restatement vs the oracle's loop version."""
+    sb = _sb()
+    rng = np.random.default_rng(29)
+    pw = synth_pwms(rng, 40, 5, 14)
+    seq = rand_seq(rng, 400)
+    pos = rng.integers(0, 400, size=50)
+    pos[:4] = [0, 1, 398, 399]
+    alts = [("ACGT".replace(seq[p], ""))[rng.integers(0, 3)] for p in pos]
+    ref_max, alt_max = sb.variant.variant_window_scores([seq], np.zeros(50, dtype=np.int32), pos, alts, pw)
+    e_ref, e_alt = so.variant_window_scan(seq, pos, alts, list(pw.weights))
+    np.testing.assert_allclose(ref_max, e_ref, rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(alt_max, e_alt, rtol=1e-5, atol=2e-5)
