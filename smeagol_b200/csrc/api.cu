@@ -66,7 +66,32 @@ struct smg_pwmset {
     int32_t* d_wide = nullptr;
 };
 
-static const int kDualMaxWidth = 16;  // PWMs up to this width keep both strands in one lane (float2 pairs)
+static const int kDualMaxWidth = 16;
+
+// side streams used to run the per-width-bucket launches of one smg_scan call concurrently (per device)
+struct StreamPool {
+    static const int kSide = 7;
+    cudaStream_t side[kSide];
+    cudaEvent_t fork;
+    cudaEvent_t join[kSide];
+    bool ok = false;
+};
+static StreamPool g_pools[64];
+static StreamPool* get_pool()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64) return nullptr;
+    StreamPool& sp = g_pools[dev];
+    if (!sp.ok) {
+        for (int i = 0; i < StreamPool::kSide; ++i) {
+            if (cudaStreamCreateWithFlags(&sp.side[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&sp.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        if (cudaEventCreateWithFlags(&sp.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        sp.ok = true;
+    }
+    return &sp;
+}  // PWMs up to this width keep both strands in one lane (float2 pairs)
 
 // ------------------------------------------------------------------------------------------ kernels
 static __constant__ uint8_t c_lut[256];
@@ -503,16 +528,28 @@ int smg_scan(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amask, 
     p.near = d_near; p.near_cap = near_cap; p.counts = d_counts;
     p.counters = reinterpret_cast<unsigned long long*>(d_counters);
     cudaStream_t st = (cudaStream_t)stream;
+    // Width buckets are independent: fork them onto side streams so that their tail waves overlap, join on `st`.
+    StreamPool* pool = get_pool();
+    if (!pool) return fail(SMG_ERR_CUDA, "smg_scan: cannot create the side streams");
+    SMG_CUDA(cudaEventRecord(pool->fork, st));
+    int bi = 0;
     for (const Bucket& b : s->buckets) {
         smg_launch_fn fn = smg_get_launcher(b.wb, b.dual);
         if (!fn) return fail(SMG_ERR_INVALID, "smg_scan: no kernel for padded width " + std::to_string(b.wb));
-        p.first_group = b.first_group;
+        cudaStream_t bs = (bi == 0) ? st : pool->side[(bi - 1) % StreamPool::kSide];
+        if (bi > 0 && bi <= StreamPool::kSide) SMG_CUDA(cudaStreamWaitEvent(bs, pool->fork, 0));
         for (int g0 = 0; g0 < b.n_groups; g0 += 65535) {  // gridDim.y limit
             ScanParams q = p;
             q.first_group = b.first_group + g0;
-            fn(q, n_chunks, std::min(65535, b.n_groups - g0), st);
+            fn(q, n_chunks, std::min(65535, b.n_groups - g0), bs);
             SMG_LAUNCH_CHECK("scan_regtab_kernel");
         }
+        ++bi;
+    }
+    const int used = std::min(bi - 1, (int)StreamPool::kSide);
+    for (int i = 0; i < used; ++i) {
+        SMG_CUDA(cudaEventRecord(pool->join[i], pool->side[i]));
+        SMG_CUDA(cudaStreamWaitEvent(st, pool->join[i], 0));
     }
     if (!s->wide.empty()) {
         scan_wide_kernel<<<(unsigned)n_chunks, 128, 0, st>>>(p, s->d_wide, (int)s->wide.size());

@@ -132,46 +132,56 @@ __global__ void __launch_bounds__(32) scan_regtab_kernel(const ScanParams p)
         __syncwarp();
     };
 
-    // one completed window score `v` of strand `st` for window start `s` (warp-uniform s)
-    auto emit = [&](const float v, const int s, const int st) {
-        const bool in_range = (s >= c0) & (s < c1);
-        const bool cand = in_range && (v > thr_lo) && (s <= smax) && (DUAL ? ((p.strands >> st) & 1) : true);
-        const unsigned cm = __ballot_sync(SMG_FULL_MASK, cand);
-        if (cm == 0) return;
-        const bool hit = cand && (v > thr_hi);
-        if (hit) {
-            if (st) ++cnt1; else ++cnt0;
-        }
-        if (cand && !hit) {  // near-threshold band: defer to the fp64 adjudicator
-            const unsigned long long i = atomicAdd(&p.counters[SMG_CTR_NEAR], 1ull);
-            if (i < p.near_cap) {
-                smg_near_t n;
-                n.row = ch.row; n.motif = motif; n.strand = st; n.start = s; n.score = v; n.reserved = 0;
-                p.near[i] = n;
-            }
-        }
-        if (want_hits) {
-            const unsigned hm = __ballot_sync(SMG_FULL_MASK, hit);
-            if (hm) {
-                if (hit) {
-                    const long long pos = st ? (smax64 - (long long)s) : (row.g_off + (long long)s);
-                    const int slot = nst + __popc(hm & lt_mask);
-                    s_keys[slot] = (st ? rowkey1 : rowkey0) | ((unsigned long long)pos << p.motif_bits) |
-                                   (unsigned long long)(unsigned)motif;
-                    s_scores[slot] = v;
+    // Candidate handling (cold path).  `bits` is this lane's mask of candidate outputs among o[0..n_out): bit
+    // (DUAL ? 2*u + strand : u) is set iff that completed window score exceeded thr_lo.  Every pass of the loop
+    // takes ONE candidate per lane (lanes may be at different (u, strand)), so the common case is a single pass:
+    // range / trim checks, definite-vs-near split, per-lane counters, ballot-compacted append to the warp stage.
+    auto handle = [&](unsigned bits, const V* o, const int s_blk) {
+        while (__any_sync(SMG_FULL_MASK, bits != 0u)) {
+            const bool have = bits != 0u;
+            const int bit = __ffs((int)bits) - 1;
+            bits &= bits - 1u;
+            const int u = DUAL ? (bit >> 1) : bit;
+            const int st = DUAL ? (bit & 1) : my_strand;
+            float v = vget(o[0], 0);
+#pragma unroll
+            for (int i = 0; i < kU; ++i) {
+                if (DUAL) {
+                    if (bit == 2 * i) v = vget(o[i], 0);
+                    if (bit == 2 * i + 1) v = vget(o[i], 1);
+                } else {
+                    if (bit == i) v = vget(o[i], 0);
                 }
-                nst += __popc(hm);
-                __syncwarp();
-                if (nst > kStageFlush) flush();
             }
-        }
-    };
-    auto emit_v = [&](const V o, const int s) {
-        if (DUAL) {
-            emit(vget(o, 0), s, 0);
-            emit(vget(o, 1), s, 1);
-        } else {
-            emit(vget(o, 0), s, my_strand);
+            const int s = s_blk + u;
+            const bool cand = have && (s >= c0) && (s < c1) && (s <= smax) && (DUAL ? ((p.strands >> st) & 1) : true);
+            const bool hit = cand && (v > thr_hi);
+            if (hit) {
+                if (st) ++cnt1; else ++cnt0;
+            }
+            if (cand && !hit) {  // near-threshold band: defer to the fp64 adjudicator
+                const unsigned long long i = atomicAdd(&p.counters[SMG_CTR_NEAR], 1ull);
+                if (i < p.near_cap) {
+                    smg_near_t n;
+                    n.row = ch.row; n.motif = motif; n.strand = st; n.start = s; n.score = v; n.reserved = 0;
+                    p.near[i] = n;
+                }
+            }
+            if (want_hits) {
+                const unsigned hm = __ballot_sync(SMG_FULL_MASK, hit);
+                if (hm) {
+                    if (hit) {
+                        const long long pos = st ? (smax64 - (long long)s) : (row.g_off + (long long)s);
+                        const int slot = nst + __popc(hm & lt_mask);
+                        s_keys[slot] = (st ? rowkey1 : rowkey0) | ((unsigned long long)pos << p.motif_bits) |
+                                       (unsigned long long)(unsigned)motif;
+                        s_scores[slot] = v;
+                    }
+                    nst += __popc(hm);
+                    __syncwarp();
+                    if (nst > kStageFlush) flush();
+                }
+            }
         }
     };
 
@@ -196,15 +206,25 @@ __global__ void __launch_bounds__(32) scan_regtab_kernel(const ScanParams p)
 #pragma unroll
                 for (int u = 1; u < kU; ++u) m = vmax3(m, o[u]);
                 if (__any_sync(SMG_FULL_MASK, m > thr_lo)) {
+                    unsigned bits = 0;
 #pragma unroll
-                    for (int u = 0; u < kU; ++u) emit_v(o[u], s_base + blk * kU + u);
+                    for (int u = 0; u < kU; ++u) {
+                        if (DUAL) {
+                            bits |= (vget(o[u], 0) > thr_lo ? 1u : 0u) << (2 * u);
+                            bits |= (vget(o[u], 1) > thr_lo ? 1u : 0u) << (2 * u + 1);
+                        } else {
+                            bits |= (vget(o[u], 0) > thr_lo ? 1u : 0u) << u;
+                        }
+                    }
+                    handle(bits, o, s_base + blk * kU);
                 }
             }
         } else {
             // ---- generic path: IUPAC ambiguity codes, 'Z', and the padding past the end of the row
 #pragma unroll 1
             for (int j = 0; j < 16; ++j) {
-                V o;
+                V oo[kU];
+                V& o = oo[0];
                 if (((am >> j) & 1u) == 0) {
                     const uint32_t b = (w >> (2 * j)) & 3u;
                     SMG_SWITCH_STEP(b, o);
@@ -218,7 +238,13 @@ __global__ void __launch_bounds__(32) scan_regtab_kernel(const ScanParams p)
                         r[k] = vadd(r[k - 1], vmix(e0, e1, e2, e3, t[k][0], t[k][1], t[k][2], t[k][3]));
                     r[0] = vmix(e0, e1, e2, e3, t[0][0], t[0][1], t[0][2], t[0][3]);
                 }
-                if (__any_sync(SMG_FULL_MASK, vmax(o) > thr_lo)) emit_v(o, s_base + j);
+                if (__any_sync(SMG_FULL_MASK, vmax(o) > thr_lo)) {
+                    unsigned bits = vget(o, 0) > thr_lo ? 1u : 0u;
+                    if (DUAL) bits |= (vget(o, 1) > thr_lo ? 2u : 0u);
+#pragma unroll
+                    for (int u = 1; u < kU; ++u) oo[u] = o;
+                    handle(bits, oo, s_base + j);
+                }
             }
         }
         w = wn;

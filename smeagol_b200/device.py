@@ -47,6 +47,19 @@ def _as_bytes(seq):
     return np.frombuffer(str(seq).encode("latin-1"), dtype=np.uint8)
 
 
+def flatten_rows(arrs, pinned=True):
+    """Copy uint8 rows into one host buffer with 16-byte aligned row starts -> (tensor, src_off)."""
+    lens = np.array([a.shape[0] for a in arrs], dtype=np.int64)
+    padded = (lens + 15) // 16 * 16
+    src_off = np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.int64)
+    total_src = int(padded.sum())
+    host = torch.empty(max(total_src, 16), dtype=torch.uint8, pin_memory=pinned)
+    hnp = host.numpy()
+    for a, o in zip(arrs, src_off):
+        hnp[o:o + a.shape[0]] = a
+    return host, src_off
+
+
 class SeqBatch:
     """Rows packed on the GPU at 2 bits/base + 1-bit ambiguity mask (+ uint8 codes only if ambiguity exists).
 
@@ -56,14 +69,24 @@ class SeqBatch:
     (chunked or multi-GPU scans); n_avail is the row's length (owned part + right halo).
     """
 
-    def __init__(self, seqs, kind="ascii", segments=None, device=None, pinned=True):
+    def __init__(self, seqs, kind="ascii", segments=None, device=None, pinned=True, flat=None):
+        """flat=(host_uint8_tensor, src_off, lens): rows already laid out in one (pinned) host buffer, row r at
+        src_off[r] (multiples of 16), so that no host-side gather is needed (used by the end-to-end benchmark)."""
         self.device = _require_cuda(device)
         lib = _lib.load()
-        arrs = [_as_bytes(s) for s in seqs]
-        n_rows = len(arrs)
-        if n_rows == 0:
-            raise ValueError("SeqBatch needs at least one row")
-        lens = np.array([a.shape[0] for a in arrs], dtype=np.int64)
+        if flat is None:
+            arrs = [_as_bytes(s) for s in seqs]
+            if len(arrs) == 0:
+                raise ValueError("SeqBatch needs at least one row")
+            lens = np.array([a.shape[0] for a in arrs], dtype=np.int64)
+            host, src_off = flatten_rows(arrs, pinned)
+        else:
+            host, src_off, lens = flat
+            lens = np.asarray(lens, dtype=np.int64)
+            src_off = np.asarray(src_off, dtype=np.int64)
+            arrs = None
+        n_rows = len(lens)
+        total_src = host.numel()
         if lens.max() >= 2 ** 31 - 256:
             raise ValueError("rows longer than 2^31 bases must be split into segments")
         rows = np.zeros(n_rows, dtype=ROW_DTYPE)
@@ -78,12 +101,6 @@ class SeqBatch:
             seg = np.asarray(segments, dtype=np.int64).reshape(n_rows, 3)
             rows["g_off"], rows["g_len"], rows["n_own"] = seg[:, 0], seg[:, 1], seg[:, 2]
         self.total_words = int(row_words.sum())
-        src_off = np.concatenate([[0], np.cumsum((lens + 15) // 16 * 16)[:-1]]).astype(np.int64)
-        total_src = int(src_off[-1] + (lens[-1] + 15) // 16 * 16)
-        host = torch.empty(max(total_src, 16), dtype=torch.uint8, pin_memory=pinned)
-        hnp = host.numpy()
-        for a, o in zip(arrs, src_off):
-            hnp[o:o + a.shape[0]] = a
         self.h2d_bytes = int(total_src)
         d_src = host.to(self.device, non_blocking=True)
         self.rows_host = rows
@@ -100,8 +117,7 @@ class SeqBatch:
                    "smg_pack")
         st = status.cpu().numpy()
         if st[0] >= 0:
-            r = int(np.searchsorted(src_off, st[0], side="right") - 1)
-            bad = arrs[r][int(st[0] - src_off[r])]
+            bad = int(host[int(st[0])])
             raise KeyError(chr(int(bad)) if kind == "ascii" else int(bad))
         self.has_ambiguity = bool(st[1])
         self.codes = codes if self.has_ambiguity else None
@@ -231,83 +247,128 @@ def pick_chunk_len(total_own, n_groups, target_ctas=148 * 16 * 8):
     return int(min(4096, max(256, c)))
 
 
+class ScanPlan:
+    """A prepared fused scan: all device buffers allocated once, kernels enqueued without host synchronisation.
+
+    launch() enqueues (counter/count reset, smg_scan, smg_adjudicate) on the current stream; finish() reads the
+    counters (one small D2H), regrows and relaunches on overflow (never truncates), and sorts the hits.
+    """
+
+    def __init__(self, pwmset, batch, thr64, strands, out_rows, n_out_rows, want_hits=True, want_counts=True,
+                 adjudicate=True, chunk_len=None, hit_cap=None, near_cap=None):
+        self.lib = _lib.load()
+        self.pwmset, self.batch = pwmset, batch
+        dev = batch.device
+        M = pwmset.n_motifs
+        thr64 = np.ascontiguousarray(thr64, dtype=np.float64)
+        assert thr64.shape == (M,)
+        lo, hi = threshold_bounds(thr64, pwmset.abs_scale, adjudicate)
+        self.motif_bits = _bits(M)
+        self.pos_bits = _bits(batch.max_g_len + 1)
+        self.row_bits = _bits(n_out_rows)
+        if self.motif_bits + self.pos_bits + self.row_bits > 63:
+            raise ValueError("hit key does not fit in 63 bits (rows=%d, length=%d, motifs=%d)"
+                             % (n_out_rows, batch.max_g_len, M))
+        self.chunk_len = pick_chunk_len(batch.total_own, pwmset.n_groups) if chunk_len is None else int(chunk_len)
+        chunks = batch.chunks(self.chunk_len)
+        self.n_chunks = len(chunks)
+        self.d_chunks = _to_dev(chunks, dev) if len(chunks) else torch.zeros(8, dtype=torch.uint8, device=dev)
+        self.d_lo = torch.from_numpy(lo).to(dev)
+        self.d_hi = torch.from_numpy(hi).to(dev)
+        self.d_thr = torch.from_numpy(thr64).to(dev)
+        self.d_out_rows = torch.from_numpy(np.ascontiguousarray(out_rows, dtype=np.int32)).to(dev)
+        self.strands = int(strands)
+        self.adjudicate = adjudicate
+        self.want_hits, self.want_counts = want_hits, want_counts
+        cells = batch.total_own * M * bin(self.strands).count("1")
+        self.hit_cap = int(min(max(1 << 16, cells * 0.004), 1 << 31)) if hit_cap is None else int(hit_cap)
+        self.near_cap = (1 << 16) if near_cap is None else int(near_cap)
+        self.counts = torch.zeros((batch.n_rows, M, 2), dtype=torch.int32, device=dev) if want_counts else None
+        self.counters = torch.zeros(_lib.N_COUNTERS, dtype=torch.int64, device=dev)
+        self._alloc()
+
+    def _alloc(self):
+        dev = self.batch.device
+        self.keys = torch.empty(self.hit_cap, dtype=torch.int64, device=dev) if self.want_hits else None
+        self.scores = torch.empty(self.hit_cap, dtype=torch.float32, device=dev) if self.want_hits else None
+        self.near = torch.empty(self.near_cap * _lib.NEAR_BYTES, dtype=torch.uint8, device=dev)
+
+    @property
+    def key_bits(self):
+        return self.motif_bits + self.pos_bits + self.row_bits
+
+    def launch(self):
+        b, lib = self.batch, self.lib
+        self.counters.zero_()
+        if self.counts is not None:
+            self.counts.zero_()
+        _lib.check(lib.smg_scan(self.pwmset.handle, _ptr(b.packed), _ptr(b.amask), _ptr(b.codes), _ptr(b.d_rows), b.n_rows,
+                                _ptr(self.d_out_rows), _ptr(self.d_chunks), self.n_chunks, self.chunk_len, self.strands,
+                                _ptr(self.d_lo), _ptr(self.d_hi), self.pos_bits, self.motif_bits, _ptr(self.keys),
+                                _ptr(self.scores), self.hit_cap, _ptr(self.near), self.near_cap, _ptr(self.counts),
+                                _ptr(self.counters), _stream()), "smg_scan")
+        if self.adjudicate:
+            self.launch_adjudicate()
+
+    def launch_adjudicate(self):
+        b, lib = self.batch, self.lib
+        _lib.check(lib.smg_adjudicate(self.pwmset.handle, _ptr(b.packed), _ptr(b.amask), _ptr(b.codes), _ptr(b.d_rows),
+                                      _ptr(self.d_out_rows), _ptr(self.d_thr), _ptr(self.near), self.near_cap, self.pos_bits,
+                                      self.motif_bits, _ptr(self.keys), _ptr(self.scores), self.hit_cap, _ptr(self.counts),
+                                      _ptr(self.counters), _stream()), "smg_adjudicate")
+
+    def finish(self, sort=True):
+        while True:
+            c = self.counters.cpu().numpy()
+            n_app, n_near = int(c[_lib.CTR_HITS_APPENDED]), int(c[_lib.CTR_NEAR])
+            grow = False
+            if n_near > self.near_cap:
+                self.near_cap = int(n_near * 1.25) + 1024
+                grow = True
+            if self.want_hits and n_app > self.hit_cap:
+                self.hit_cap = int(n_app * 1.1) + 1024
+                grow = True
+            if not grow:
+                break
+            self._alloc()
+            self.launch()
+        n_hits = n_app if self.want_hits else 0
+        stats = {"n_definite": int(c[_lib.CTR_DEFINITE]), "n_near": n_near,
+                 "n_adjudicated_accepted": int(c[_lib.CTR_ADJ_ACCEPTED]),
+                 "n_hits_total": int(c[_lib.CTR_DEFINITE]) + int(c[_lib.CTR_ADJ_ACCEPTED]), "chunk_len": self.chunk_len,
+                 "n_chunks": self.n_chunks, "hit_cap": self.hit_cap, "near_cap": self.near_cap}
+        keys, scores = self.keys, self.scores
+        if self.want_hits and sort and n_hits > 0:
+            keys, scores = sort_hits(keys, scores, n_hits, self.key_bits)
+        return ScanResult(keys, scores, n_hits, self.counts, self.pos_bits, self.motif_bits, stats)
+
+
 def scan(pwmset, batch, thr64, strands, out_rows, n_out_rows, want_hits=True, want_counts=True, adjudicate=True,
-         chunk_len=None, hit_cap=None, near_cap=None, sort=True, workspace=None):
+         chunk_len=None, hit_cap=None, near_cap=None, sort=True):
     """Fused two-strand scan of a SeqBatch against a DevicePWMSet.
 
     thr64: per-PWM thresholds (frac * max_scores, computed by the caller exactly as models.py:141 does).
     out_rows: int32 (n_rows, 2) output row of (row, strand) in the reference's row order; n_out_rows their count.
     Returns a ScanResult.  Hit-buffer overflow is detected and the scan retried with a larger buffer, never truncated.
     """
-    lib = _lib.load()
-    dev = batch.device
-    M = pwmset.n_motifs
-    thr64 = np.ascontiguousarray(thr64, dtype=np.float64)
-    assert thr64.shape == (M,)
-    lo, hi = threshold_bounds(thr64, pwmset.abs_scale, adjudicate)
-    motif_bits = _bits(M)
-    pos_bits = _bits(batch.max_g_len + 1)
-    row_bits = _bits(n_out_rows)
-    if motif_bits + pos_bits + row_bits > 63:
-        raise ValueError("hit key does not fit in 63 bits (rows=%d, length=%d, motifs=%d)" % (n_out_rows, batch.max_g_len, M))
-    if chunk_len is None:
-        chunk_len = pick_chunk_len(batch.total_own, pwmset.n_groups)
-    chunks = batch.chunks(chunk_len)
-    d_chunks = _to_dev(chunks, dev) if len(chunks) else torch.zeros(8, dtype=torch.uint8, device=dev)
-    d_lo = torch.from_numpy(lo).to(dev)
-    d_hi = torch.from_numpy(hi).to(dev)
-    d_thr = torch.from_numpy(thr64).to(dev)
-    d_out_rows = torch.from_numpy(np.ascontiguousarray(out_rows, dtype=np.int32)).to(dev)
-    n_strands = bin(strands).count("1")
-    cells = batch.total_own * M * n_strands
-    if hit_cap is None:
-        hit_cap = int(min(max(1 << 16, cells * 0.004), 1 << 31))
-    if near_cap is None:
-        near_cap = 1 << 16
-    counts = torch.zeros((batch.n_rows, M, 2), dtype=torch.int32, device=dev) if want_counts else None
-    while True:
-        counters = torch.zeros(_lib.N_COUNTERS, dtype=torch.int64, device=dev)
-        keys = torch.empty(hit_cap, dtype=torch.int64, device=dev) if want_hits else None
-        scores = torch.empty(hit_cap, dtype=torch.float32, device=dev) if want_hits else None
-        near = torch.empty(near_cap * _lib.NEAR_BYTES, dtype=torch.uint8, device=dev)
-        if counts is not None:
-            counts.zero_()
-        _lib.check(lib.smg_scan(pwmset.handle, _ptr(batch.packed), _ptr(batch.amask), _ptr(batch.codes), _ptr(batch.d_rows),
-                                batch.n_rows, _ptr(d_out_rows), _ptr(d_chunks), len(chunks), chunk_len, strands, _ptr(d_lo),
-                                _ptr(d_hi), pos_bits, motif_bits, _ptr(keys), _ptr(scores), hit_cap, _ptr(near), near_cap,
-                                _ptr(counts), _ptr(counters), _stream()), "smg_scan")
-        if adjudicate:
-            _lib.check(lib.smg_adjudicate(pwmset.handle, _ptr(batch.packed), _ptr(batch.amask), _ptr(batch.codes),
-                                          _ptr(batch.d_rows), _ptr(d_out_rows), _ptr(d_thr), _ptr(near), near_cap, pos_bits,
-                                          motif_bits, _ptr(keys), _ptr(scores), hit_cap, _ptr(counts), _ptr(counters),
-                                          _stream()), "smg_adjudicate")
-        c = counters.cpu().numpy()
-        n_app, n_near = int(c[_lib.CTR_HITS_APPENDED]), int(c[_lib.CTR_NEAR])
-        if n_near > near_cap:
-            near_cap = int(n_near * 1.25) + 1024
-            continue
-        if want_hits and n_app > hit_cap:
-            hit_cap = int(n_app * 1.1) + 1024
-            continue
-        break
-    n_hits = n_app if want_hits else 0
-    stats = {"n_definite": int(c[_lib.CTR_DEFINITE]), "n_near": n_near, "n_adjudicated_accepted": int(c[_lib.CTR_ADJ_ACCEPTED]),
-             "n_hits_total": int(c[_lib.CTR_DEFINITE]) + int(c[_lib.CTR_ADJ_ACCEPTED]), "chunk_len": chunk_len,
-             "n_chunks": len(chunks), "hit_cap": hit_cap, "near_cap": near_cap}
-    if want_hits and sort and n_hits > 0:
-        keys, scores = sort_hits(keys, scores, n_hits, motif_bits + pos_bits + row_bits)
-    return ScanResult(keys, scores, n_hits, counts, pos_bits, motif_bits, stats)
+    plan = ScanPlan(pwmset, batch, thr64, strands, out_rows, n_out_rows, want_hits, want_counts, adjudicate, chunk_len,
+                    hit_cap, near_cap)
+    plan.launch()
+    return plan.finish(sort=sort)
 
 
-def sort_hits(keys, scores, n, key_bits):
+def sort_hits(keys, scores, n, key_bits, keys_out=None, scores_out=None, temp=None):
     lib = _lib.load()
     dev = keys.device
-    keys_out = torch.empty(n, dtype=torch.int64, device=dev)
-    scores_out = torch.empty(n, dtype=torch.float32, device=dev)
+    if keys_out is None:
+        keys_out = torch.empty(n, dtype=torch.int64, device=dev)
+        scores_out = torch.empty(n, dtype=torch.float32, device=dev)
     tb = ctypes.c_uint64(0)
     _lib.check(lib.smg_sort_hits(_ptr(keys), _ptr(scores), _ptr(keys_out), _ptr(scores_out), n, key_bits, None,
                                  ctypes.byref(tb), _stream()), "smg_sort_hits(query)")
-    temp = torch.empty(max(int(tb.value), 16), dtype=torch.uint8, device=dev)
+    if temp is None or temp.numel() < int(tb.value):
+        temp = torch.empty(max(int(tb.value), 16), dtype=torch.uint8, device=dev)
+    tb = ctypes.c_uint64(temp.numel())
     _lib.check(lib.smg_sort_hits(_ptr(keys), _ptr(scores), _ptr(keys_out), _ptr(scores_out), n, key_bits, _ptr(temp),
                                  ctypes.byref(tb), _stream()), "smg_sort_hits")
     return keys_out, scores_out
