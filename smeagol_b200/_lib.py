@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsmeagol_b200.so")
+LIB_PATH = os.environ.get("SMEAGOL_B200_LIB", os.path.join(_HERE, "libsmeagol_b200.so"))  # env: tuning builds
 
 SMG_OK = 0
 CTR_HITS_APPENDED, CTR_NEAR, CTR_DEFINITE, CTR_ADJ_ACCEPTED, CTR_LAUNCHES = 0, 1, 2, 3, 4

@@ -50,7 +50,10 @@ __device__ __forceinline__ float vmix(const float e0, const float e1, const floa
 
 constexpr int kStageCap = 128;   // per-warp staged hits
 constexpr int kStageFlush = 64;  // flush when more than this many are staged (one event adds <= 32)
-constexpr int kU = 4;            // steps between threshold checks on the ACGT fast path
+#ifndef SMG_KU
+#define SMG_KU 4
+#endif
+constexpr int kU = SMG_KU;       // steps between threshold checks on the ACGT fast path (divides 16)
 
 // one shift-register step for base B (compile-time); O receives the completed window score
 #define SMG_STEP(B, O)                                                                        \
@@ -67,6 +70,29 @@ constexpr int kU = 4;            // steps between threshold checks on the ACGT f
     case 2: SMG_STEP(2, O); break; \
     default: SMG_STEP(3, O); break; \
     }
+
+// two bases (A then B) per dispatch: r''[k] = (r[k-2] + T[k-1][A]) + T[k][B] -- the same association as two
+// single steps, so scores stay bit-identical; halves the number of (latency-bound) uniform branch chains per base
+#define SMG_STEP2(A, B, O1, O2)                                                                                   \
+    {                                                                                                             \
+        O1 = vadd(r[WB - 2], t[WB - 1][A]);                                                                       \
+        if (WB >= 3) O2 = vadd(vadd(r[WB >= 3 ? WB - 3 : 0], t[WB - 2][A]), t[WB - 1][B]);                        \
+        else O2 = vadd(t[0][A], t[1][B]);                                                                         \
+        _Pragma("unroll") for (int k = WB - 2; k >= 2; --k) r[k] = vadd(vadd(r[k - 2], t[k - 1][A]), t[k][B]);    \
+        if (WB >= 3) r[WB >= 3 ? 1 : 0] = vadd(t[0][A], t[1][B]);                                                 \
+        r[0] = t[0][B];                                                                                           \
+    }
+#define SMG_CASE2(n) case n: SMG_STEP2(((n) & 3), ((n) >> 2), O1, O2); break;
+#define SMG_SWITCH_STEP2(q, O1, O2)                                                                               \
+    switch (q) {                                                                                                  \
+        SMG_CASE2(0) SMG_CASE2(1) SMG_CASE2(2) SMG_CASE2(3) SMG_CASE2(4) SMG_CASE2(5) SMG_CASE2(6) SMG_CASE2(7)   \
+        SMG_CASE2(8) SMG_CASE2(9) SMG_CASE2(10) SMG_CASE2(11) SMG_CASE2(12) SMG_CASE2(13) SMG_CASE2(14)           \
+    default: SMG_STEP2(3, 3, O1, O2); break;                                                                      \
+    }
+
+#ifndef SMG_BPD2_MAX_WB
+#define SMG_BPD2_MAX_WB 0  // padded widths up to this use the two-bases-per-dispatch fast path (measured: not a win, off)
+#endif
 
 template <int WB, bool DUAL>
 __global__ void __launch_bounds__(32) scan_regtab_kernel(const ScanParams p)
@@ -196,10 +222,22 @@ __global__ void __launch_bounds__(32) scan_regtab_kernel(const ScanParams p)
 #pragma unroll 1
             for (int blk = 0; blk < 16 / kU; ++blk) {
                 V o[kU];
+                if (DUAL && WB <= SMG_BPD2_MAX_WB) {
 #pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    const uint32_t b = (w >> (2 * u)) & 3u;
-                    SMG_SWITCH_STEP(b, o[u]);
+                    for (int u = 0; u < kU; u += 2) {
+                        const uint32_t q = (w >> (2 * u)) & 15u;
+#define O1 o[u]
+#define O2 o[u + 1]
+                        SMG_SWITCH_STEP2(q, O1, O2);
+#undef O1
+#undef O2
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const uint32_t b = (w >> (2 * u)) & 3u;
+                        SMG_SWITCH_STEP(b, o[u]);
+                    }
                 }
                 w >>= 2 * kU;
                 float m = vmax(o[0]);
