@@ -186,7 +186,8 @@ def main():
     keys_out = torch.empty(n_hits, dtype=torch.int64, device=device)
     scores_out = torch.empty(n_hits, dtype=torch.float32, device=device)
     sort_tmp = torch.empty(64 << 20, dtype=torch.uint8, device=device)
-    gathered = torch.empty((world,) + tuple(plan.counts.shape), dtype=torch.int32, device=device) if world > 1 else None
+    gathered = (torch.empty((world * plan.counts.shape[0],) + tuple(plan.counts.shape[1:]), dtype=torch.int32, device=device)
+                if world > 1 else None)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
 
     def step(ev=None):

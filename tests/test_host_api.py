@@ -1,0 +1,124 @@
+"""CPU tests of the host-side mirror of the reference API (no GPU): encode / SeqEncoding / SeqGroups / FASTA /
+threshold bounds / key layout / count melting.  Restates tests/test_encode.py and the schema tests of
+tests/test_scan.py of the reference against this package."""
+import gzip
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import smeagol_b200 as sb
+from golden_util import assert_frame_matches, golden, pwm_df
+from smeagol_b200 import device as dev
+from smeagol_b200.encode import SeqEncoding, SeqGroups, integer_encode, one_hot_encode
+from smeagol_b200.seqrecord import Seq, SeqRecord
+
+
+def test_integer_encode():
+    """reference tests/test_encode.py:13-23"""
+    record = SeqRecord(Seq("ACGTNWSMKRYBDHVZ"), id="id", name="name")
+    assert np.all(integer_encode(record, rc=False) == [1, 2, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 0])
+    assert integer_encode(record).dtype == np.float32
+    with pytest.raises(KeyError):
+        integer_encode(SeqRecord(Seq("ACGE")), rc="none")
+    assert np.all(integer_encode(SeqRecord(Seq("AGCAU")), rc=True) == [1, 5, 3, 2, 5])
+    assert np.all(integer_encode("ACGT", rc=True) == [1, 2, 3, 4])
+    with pytest.raises(TypeError):
+        integer_encode(5)
+    G = golden()["test_encode"]
+    np.testing.assert_array_equal(one_hot_encode("ACGTN"), np.array(G["one_hot_ACGTN"], dtype=np.float32))
+
+
+def test_SeqEncoding():
+    """reference tests/test_encode.py:26-51"""
+    records = [SeqRecord(Seq("AGC"), id="id1", name="name1"), SeqRecord(Seq("ACA"), id="id2", name="name2")]
+    result = SeqEncoding(records, sense="+")
+    assert result.len == 3
+    assert np.all(result.ids == ["id1", "id2"]) and np.all(result.names == ["name1", "name2"])
+    assert np.all(result.seqs == np.array([[1, 3, 2], [1, 2, 1]])) and np.all(result.senses == ["+", "+"])
+    assert type(result.senses) == np.ndarray and type(result.ids) == np.ndarray and type(result.names) == np.ndarray
+    result = SeqEncoding(records, sense="+", rcomp="only")
+    assert np.all(result.seqs == np.array([[3, 2, 4], [4, 3, 4]])) and np.all(result.senses == ["-", "-"])
+    result = SeqEncoding(records, sense="+", rcomp="both")
+    assert np.all(result.ids == ["id1", "id2", "id1", "id2"])
+    assert np.all(result.names == ["name1", "name2", "name1", "name2"])
+    assert np.all(result.seqs == np.array([[1, 3, 2], [1, 2, 1], [3, 2, 4], [4, 3, 4]]))
+    assert np.all(result.senses == ["+", "+", "-", "-"])
+    with pytest.raises(ValueError):
+        SeqEncoding([SeqRecord(Seq("AGC"), id="a", name="a"), SeqRecord(Seq("AG"), id="b", name="b")], sense="+")
+    with pytest.raises(AssertionError):
+        SeqEncoding(records, sense="+", rcomp="sideways")
+    for rc in ("none", "only", "both"):
+        e = SeqEncoding(records, sense="+", rcomp=rc)
+        g = golden()["test_encode"]["SeqEncoding_" + rc]
+        assert list(e.ids) == g["ids"] and list(e.senses) == g["senses"] and e.len == g["len"]
+        np.testing.assert_array_equal(e.seqs, np.array(g["seqs"]))
+
+
+def test_SeqGroups_and_fasta(tmp_path):
+    """reference tests/test_encode.py:54-85 (test.fa.gz content is replayed from the golden file)"""
+    fa = os.path.join(str(tmp_path), "test.fa.gz")
+    with gzip.open(fa, "wt") as f:
+        for rid, name, seq in golden()["test_encode"]["test_fa"]:
+            f.write(">%s Test sequence\n%s\n" % (rid, seq))
+    result = SeqGroups(fa, sense="+")
+    assert [g.records[0] for g in result.seqs] == ["ATTAAATA", "CAAAATCTTTAGGATTAGCAC"]
+    assert [g.ids[0] for g in result.seqs] == ["Seg1", "Seg2"] and [g.names[0] for g in result.seqs] == ["Seg1", "Seg2"]
+    np.testing.assert_array_equal(result.seqs[0].seqs, [[1, 4, 4, 1, 1, 1, 4, 1]])
+    records = [SeqRecord(Seq("AGC"), id="id1", name="name"), SeqRecord(Seq("ACA"), id="id2", name="name")]
+    result = SeqGroups(records, sense="-", rcomp="both", group_by="name")
+    assert len(result.seqs) == 1
+    expected = SeqEncoding(records, sense="-", rcomp="both")
+    assert np.all(result.seqs[0].seqs == expected.seqs) and np.all(result.seqs[0].senses == ["-", "-", "+", "+"])
+    out = os.path.join(str(tmp_path), "o.fa")
+    sb.io.write_fasta(records, out)
+    back = sb.io.read_fasta(out)
+    assert [str(r.seq) for r in back] == ["AGC", "ACA"] and [r.id for r in back] == ["id1", "id2"]
+
+
+def test_model_constants_and_thresholds():
+    """reference tests/test_models.py:38-43"""
+    model = sb.models.PWMModel(pwm_df(golden()["test_pwms"]))
+    assert np.all(model.Matrix_ids == ["x", "y", "z"]) and np.all(model.widths == [3, 5, 3])
+    assert sb.utils._equals(model.max_scores, np.array([3.33376361, 5.52770673, 2.50816981]))
+    assert model.channels == 3 and model.max_width == 5
+    with pytest.raises(AssertionError):
+        model.thresholds(1.2)
+    thr = model.thresholds(0.65)
+    lo, hi = dev.threshold_bounds(thr, np.array([10.0, 12.0, 8.0]), adjudicate=False)
+    assert np.all(lo == hi) and np.all(lo.astype(np.float64) <= thr)
+    assert np.all(np.nextafter(lo, np.float32(np.inf)).astype(np.float64) > thr)
+    lo, hi = dev.threshold_bounds(thr, np.array([10.0, 12.0, 8.0]), adjudicate=True)
+    assert np.all(lo.astype(np.float64) <= thr - 1e-5 * np.array([10.0, 12.0, 8.0]))
+    assert np.all(hi.astype(np.float64) >= thr + 1e-5 * np.array([10.0, 12.0, 8.0]))
+
+
+def test_locate_and_count_sites_schema():
+    """reference tests/test_scan.py:28-47, 73-79"""
+    G = golden()["test_scan"]
+    model = sb.models.PWMModel(pwm_df(golden()["test_pwms"]))
+    recs = [SeqRecord(Seq(s), id=i, name=n) for s, i, n in zip(G["seqs"], G["ids"], G["names"])]
+    encoding = SeqEncoding(recs, sense="+", rcomp="none")
+    thresholded = [[1, 1], [0, 0], [0, 2]]
+    res = sb.scan._locate_sites(encoding, model, thresholded, np.array([2.343, 1.929]))
+    assert_frame_matches(res, G["locate_sites"], "locate_sites")
+    assert sb.utils._equals(res.frac_score.values, np.array([0.70280927926, 0.76908668]))
+    cnt = sb.scan._count_sites(encoding, model, thresholded)
+    assert_frame_matches(cnt, G["count_sites"], "count_sites")
+    empty = sb.scan._count_sites(encoding, model, ([], [], []))
+    assert list(empty.columns) == ["Matrix_id", "width", "id", "name", "sense", "num"] and len(empty) == 0
+
+
+def test_chunks_and_row_layout_host_side():
+    lens = np.array([100, 4096, 5000, 1], dtype=np.int64)
+    rows = np.zeros(4, dtype=dev.ROW_DTYPE)
+    rows["n_own"] = lens
+
+    class B:
+        rows_host = rows
+        n_rows = 4
+    ch = dev.SeqBatch.chunks(B, 4096)
+    assert list(ch["row"]) == [0, 1, 2, 2, 3] and list(ch["start"]) == [0, 0, 0, 4096, 0]
+    assert dev.pick_chunk_len(10_000_000, 32) == 4096 and dev.pick_chunk_len(30_000, 4) == 256
+    assert dev._bits(1000) == 10 and dev._bits(1024) == 10 and dev._bits(1025) == 11 and dev._bits(1) == 1
