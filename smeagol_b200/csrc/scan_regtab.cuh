@@ -48,6 +48,7 @@ __device__ __forceinline__ float vmix(const float e0, const float e1, const floa
     return smg_mix(e0, e1, e2, e3, t0, t1, t2, t3);
 }
 
+constexpr int kQCap = 16;        // per-lane candidate queue slots (a block of kU steps adds at most 2*kU)
 constexpr int kStageCap = 128;   // per-warp staged hits
 constexpr int kStageFlush = 64;  // flush when more than this many are staged (one event adds <= 32)
 #ifndef SMG_KU
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(32) scan_regtab_kernel(const ScanParams p)
     using V = typename VecOf<DUAL>::T;
     __shared__ unsigned long long s_keys[kStageCap];
     __shared__ float s_scores[kStageCap];
+    __shared__ uint2 s_q[kQCap][32];  // per-lane candidate queues, [slot][lane] (bank-conflict free)
 
     const int lane = threadIdx.x;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -158,28 +160,26 @@ __global__ void __launch_bounds__(32) scan_regtab_kernel(const ScanParams p)
         __syncwarp();
     };
 
-    // Candidate handling (cold path).  `bits` is this lane's mask of candidate outputs among o[0..n_out): bit
-    // (DUAL ? 2*u + strand : u) is set iff that completed window score exceeded thr_lo.  Every pass of the loop
-    // takes ONE candidate per lane (lanes may be at different (u, strand)), so the common case is a single pass:
-    // range / trim checks, definite-vs-near split, per-lane counters, ballot-compacted append to the warp stage.
-    auto handle = [&](unsigned bits, const V* o, const int s_blk) {
-        while (__any_sync(SMG_FULL_MASK, bits != 0u)) {
-            const bool have = bits != 0u;
-            const int bit = __ffs((int)bits) - 1;
-            bits &= bits - 1u;
-            const int u = DUAL ? (bit >> 1) : bit;
-            const int st = DUAL ? (bit & 1) : my_strand;
-            float v = vget(o[0], 0);
-#pragma unroll
-            for (int i = 0; i < kU; ++i) {
-                if (DUAL) {
-                    if (bit == 2 * i) v = vget(o[i], 0);
-                    if (bit == 2 * i + 1) v = vget(o[i], 1);
-                } else {
-                    if (bit == i) v = vget(o[i], 0);
-                }
-            }
-            const int s = s_blk + u;
+    // Candidate handling.  Two levels keep the per-block cost low:
+    //  (1) push(): a lane whose completed window score exceeds thr_lo appends (step, strand, score) to ITS OWN
+    //      queue in shared memory -- predicated store + pointer bump, no ballot / shuffle / loop in the scan loop;
+    //  (2) drain(): when any queue is half full (and at the end of the chunk) the warp walks the queues together:
+    //      range / trim checks, definite-vs-near split, per-lane counters, ballot + prefix-popcount compaction into
+    //      the warp stage, which is appended to the global hit list with one atomic per flush.
+    const int s_origin = c0 - (WB - 1);  // window start completed by the first step of the chunk
+    int qn = 0;
+    auto push = [&](const float v, const int step_rel, const int st) {
+        s_q[qn][lane] = make_uint2(((unsigned)step_rel << 1) | (unsigned)st, __float_as_uint(v));
+        ++qn;
+    };
+    auto drain = [&]() {
+        const int maxn = __reduce_max_sync(SMG_FULL_MASK, qn);
+        for (int j = 0; j < maxn; ++j) {
+            const bool have = j < qn;
+            const uint2 e = have ? s_q[j][lane] : make_uint2(0u, 0u);
+            const float v = __uint_as_float(e.y);
+            const int st = DUAL ? (int)(e.x & 1u) : my_strand;
+            const int s = s_origin + (int)(e.x >> 1);
             const bool cand = have && (s >= c0) && (s < c1) && (s <= smax) && (DUAL ? ((p.strands >> st) & 1) : true);
             const bool hit = cand && (v > thr_hi);
             if (hit) {
@@ -209,6 +209,8 @@ __global__ void __launch_bounds__(32) scan_regtab_kernel(const ScanParams p)
                 }
             }
         }
+        qn = 0;
+        __syncwarp();
     };
 
     uint32_t w = wp[0];
@@ -244,25 +246,22 @@ __global__ void __launch_bounds__(32) scan_regtab_kernel(const ScanParams p)
 #pragma unroll
                 for (int u = 1; u < kU; ++u) m = vmax3(m, o[u]);
                 if (__any_sync(SMG_FULL_MASK, m > thr_lo)) {
-                    unsigned bits = 0;
+                    const int rel = wi * 16 + blk * kU;
 #pragma unroll
                     for (int u = 0; u < kU; ++u) {
+                        if (vget(o[u], 0) > thr_lo) push(vget(o[u], 0), rel + u, 0);
                         if (DUAL) {
-                            bits |= (vget(o[u], 0) > thr_lo ? 1u : 0u) << (2 * u);
-                            bits |= (vget(o[u], 1) > thr_lo ? 1u : 0u) << (2 * u + 1);
-                        } else {
-                            bits |= (vget(o[u], 0) > thr_lo ? 1u : 0u) << u;
+                            if (vget(o[u], 1) > thr_lo) push(vget(o[u], 1), rel + u, 1);
                         }
                     }
-                    handle(bits, o, s_base + blk * kU);
+                    if (__any_sync(SMG_FULL_MASK, qn > kQCap - 2 * kU)) drain();
                 }
             }
         } else {
             // ---- generic path: IUPAC ambiguity codes, 'Z', and the padding past the end of the row
 #pragma unroll 1
             for (int j = 0; j < 16; ++j) {
-                V oo[kU];
-                V& o = oo[0];
+                V o;
                 if (((am >> j) & 1u) == 0) {
                     const uint32_t b = (w >> (2 * j)) & 3u;
                     SMG_SWITCH_STEP(b, o);
@@ -277,11 +276,11 @@ __global__ void __launch_bounds__(32) scan_regtab_kernel(const ScanParams p)
                     r[0] = vmix(e0, e1, e2, e3, t[0][0], t[0][1], t[0][2], t[0][3]);
                 }
                 if (__any_sync(SMG_FULL_MASK, vmax(o) > thr_lo)) {
-                    unsigned bits = vget(o, 0) > thr_lo ? 1u : 0u;
-                    if (DUAL) bits |= (vget(o, 1) > thr_lo ? 2u : 0u);
-#pragma unroll
-                    for (int u = 1; u < kU; ++u) oo[u] = o;
-                    handle(bits, oo, s_base + j);
+                    if (vget(o, 0) > thr_lo) push(vget(o, 0), wi * 16 + j, 0);
+                    if (DUAL) {
+                        if (vget(o, 1) > thr_lo) push(vget(o, 1), wi * 16 + j, 1);
+                    }
+                    if (__any_sync(SMG_FULL_MASK, qn > kQCap - 2 * kU)) drain();
                 }
             }
         }
@@ -290,6 +289,7 @@ __global__ void __launch_bounds__(32) scan_regtab_kernel(const ScanParams p)
         s_base += 16;
     }
 
+    drain();
     if (want_hits && nst > 0) flush();
     if (p.counts != nullptr && motif >= 0) {
         int32_t* c = p.counts + ((size_t)ch.row * p.n_motifs + motif) * 2;
