@@ -95,8 +95,15 @@ constexpr int kU = SMG_KU;       // steps between threshold checks on the ACGT f
 #define SMG_BPD2_MAX_WB 0  // padded widths up to this use the two-bases-per-dispatch fast path (measured: not a win, off)
 #endif
 
+// Explicit register caps per instantiation (an uncapped __maxnreg__ makes ptxas spend MORE registers than its
+// default heuristic and lose occupancy; measured).  Caps sit on occupancy steps: warps/SM = 65536 / (32 * regs).
+template <int WB, bool DUAL> struct MaxRegs {
+    static constexpr int v = DUAL ? (WB <= 9 ? 128 : WB == 10 ? 144 : WB <= 13 ? 168 : WB == 14 ? 216 : WB == 15 ? 224 : 240)
+                                  : (WB <= 19 ? 144 : WB <= 26 ? 168 : 240);
+};
+
 template <int WB, bool DUAL>
-__global__ void __launch_bounds__(32) scan_regtab_kernel(const ScanParams p)
+__global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, DUAL>::v)) scan_regtab_kernel(const ScanParams p)
 {
     static_assert(WB >= 2 && WB <= SMG_MAX_REGTAB_WIDTH, "unsupported padded width");
     using V = typename VecOf<DUAL>::T;
@@ -237,8 +244,16 @@ __global__ void __launch_bounds__(32) scan_regtab_kernel(const ScanParams p)
                 } else {
 #pragma unroll
                     for (int u = 0; u < kU; ++u) {
+#ifndef SMG_SWITCH_DISPATCH  // bit tests straight off the packed word: ~5% faster than extract + switch (measured)
+                        if (w & (2u << (2 * u))) {
+                            if (w & (1u << (2 * u))) SMG_STEP(3, o[u]) else SMG_STEP(2, o[u])
+                        } else {
+                            if (w & (1u << (2 * u))) SMG_STEP(1, o[u]) else SMG_STEP(0, o[u])
+                        }
+#else
                         const uint32_t b = (w >> (2 * u)) & 3u;
                         SMG_SWITCH_STEP(b, o[u]);
+#endif
                     }
                 }
                 w >>= 2 * kU;
