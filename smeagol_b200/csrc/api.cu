@@ -11,6 +11,8 @@
 
 #include "common.cuh"
 #include "launchers.h"
+#include "variant_regtab.cuh"
+#include "variant_launchers.h"
 
 // ------------------------------------------------------------------------------------------ host-side state
 static thread_local std::string g_err;
@@ -55,6 +57,9 @@ struct smg_pwmset {
     std::vector<Group> groups;
     std::vector<Bucket> buckets;
     std::vector<int> wide;
+    std::vector<int> dual_motifs, nondual_motifs;
+    int32_t* d_dual_list = nullptr;
+    int32_t* d_nondual_list = nullptr;
     int64_t sum_padded = 0;
     float* d_nat = nullptr;
     int32_t* d_width = nullptr;
@@ -287,19 +292,23 @@ __global__ void __launch_bounds__(128) variant_sites_kernel(const ScanParams p, 
 // from global memory (L1-resident: 32 motifs x W x 4 floats), the 2W-1 bases around the SNV are warp-uniform.
 __global__ void __launch_bounds__(128) variant_windows_kernel(const ScanParams p, const int32_t* __restrict__ snv_row,
                                                               const int32_t* __restrict__ snv_pos, const uint8_t* __restrict__ snv_alt,
-                                                              const int64_t n_snv, float* __restrict__ ref_max, float* __restrict__ alt_max)
+                                                              const int64_t n_snv, float* __restrict__ ref_max, float* __restrict__ alt_max,
+                                                              const int32_t* __restrict__ motif_list, const int n_list,
+                                                              const unsigned int* __restrict__ flags)
 {
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
-    const int m = blockIdx.y * 32 + lane;
-    const bool active = m < p.n_motifs;
+    const int li = blockIdx.y * 32 + lane;
+    const bool active = li < n_list;
+    const int m = active ? motif_list[li] : 0;
     const int wm = active ? p.motif_width[m] : 0;
     const float* tab = active ? p.nat_tab + p.motif_off[m] * 4 : nullptr;
     const float ninf = __int_as_float(0xff800000);
     for (int64_t v = (int64_t)blockIdx.x * 4 + warp_in_block; v < n_snv; v += (int64_t)gridDim.x * 4) {
+        if (flags != nullptr && flags[v] == 0u) continue;
         const smg_row_t row = p.rows[snv_row[v]];
         const int64_t pos = snv_pos[v];
-        const int alt = snv_alt[v];
+        const int alt = snv_alt[v] <= 16 ? snv_alt[v] : 0;
         float rmax = ninf, amax = ninf;
         if (active) {
             const int64_t s_lo = max((int64_t)0, pos - wm + 1);
@@ -452,10 +461,12 @@ int smg_pwmset_create(const float* h_weights, const int32_t* h_widths, int32_t n
     std::vector<float> nat(h_weights, h_weights + tot * 4);
     std::vector<int32_t> wv(h_widths, h_widths + n_motifs);
     std::vector<int32_t> widev(s->wide.begin(), s->wide.end());
+    for (int m = 0; m < n_motifs; ++m) (h_widths[m] <= kDualMaxWidth ? s->dual_motifs : s->nondual_motifs).push_back(m);
+    std::vector<int32_t> dualv(s->dual_motifs.begin(), s->dual_motifs.end()), nondualv(s->nondual_motifs.begin(), s->nondual_motifs.end());
     if ((rc = upload(&s->d_nat, nat)) || (rc = upload(&s->d_width, wv)) || (rc = upload(&s->d_off, s->offs)) ||
         (rc = upload(&s->d_gtab, gtab)) || (rc = upload(&s->d_gtab_off, gtab_off)) ||
         (rc = upload(&s->d_lane_motif, lane_motif)) || (rc = upload(&s->d_lane_strand, lane_strand)) ||
-        (rc = upload(&s->d_wide, widev))) {
+        (rc = upload(&s->d_wide, widev)) || (rc = upload(&s->d_dual_list, dualv)) || (rc = upload(&s->d_nondual_list, nondualv))) {
         smg_pwmset_destroy(s);
         return rc;
     }
@@ -467,7 +478,7 @@ int smg_pwmset_destroy(smg_pwmset_t s)
 {
     if (!s) return SMG_OK;
     cudaFree(s->d_nat); cudaFree(s->d_width); cudaFree(s->d_off); cudaFree(s->d_gtab); cudaFree(s->d_gtab_off);
-    cudaFree(s->d_lane_motif); cudaFree(s->d_lane_strand); cudaFree(s->d_wide);
+    cudaFree(s->d_lane_motif); cudaFree(s->d_lane_strand); cudaFree(s->d_wide); cudaFree(s->d_dual_list); cudaFree(s->d_nondual_list);
     delete s;
     return SMG_OK;
 }
@@ -631,10 +642,38 @@ int smg_variant_windows(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t
     if (n_snv == 0) return SMG_OK;
     ScanParams p;
     fill_params(p, s, d_packed, d_amask, d_codes, d_rows, nullptr);
-    dim3 grid((unsigned)std::min<int64_t>((n_snv + 3) / 4, 148 * 64), (unsigned)((s->n_motifs + 31) / 32), 1);
-    variant_windows_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p, d_snv_row, d_snv_pos, d_snv_alt, n_snv, d_ref_max, d_alt_max);
-    SMG_LAUNCH_CHECK("variant_windows_kernel");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned nb = (unsigned)std::min<int64_t>((n_snv + 3) / 4, 148 * 64);
+    // PWMs up to kDualMaxWidth: register-table kernel (both strands per lane); SNVs it cannot take (ambiguity codes
+    // in the region, ambiguous alt) are flagged and redone by the generic kernel, as are the wider PWMs.
+    unsigned int* d_flags = nullptr;
+    if (!s->dual_motifs.empty()) {
+        SMG_CUDA(cudaMallocAsync((void**)&d_flags, (size_t)n_snv * sizeof(unsigned int), st));
+        SMG_CUDA(cudaMemsetAsync(d_flags, 0, (size_t)n_snv * sizeof(unsigned int), st));
+        smg::VariantParams vp;
+        vp.sp = p; vp.snv_row = d_snv_row; vp.snv_pos = d_snv_pos; vp.snv_alt = d_snv_alt; vp.n_snv = n_snv;
+        vp.ref_max = d_ref_max; vp.alt_max = d_alt_max; vp.slow_flags = d_flags;
+        const int blocks = (int)std::min<int64_t>(n_snv, 148 * 16 * 4);
+        for (const Bucket& b : s->buckets) {
+            if (!b.dual) continue;
+            smg_variant_launch_fn fn = smg_get_variant_launcher(b.wb);
+            if (!fn) return fail(SMG_ERR_INVALID, "smg_variant_windows: no kernel for padded width " + std::to_string(b.wb));
+            vp.sp.first_group = b.first_group;
+            fn(vp, blocks, b.n_groups, st);
+            SMG_LAUNCH_CHECK("variant_regtab_kernel");
+        }
+        dim3 gridf(nb, (unsigned)((s->dual_motifs.size() + 31) / 32), 1);
+        variant_windows_kernel<<<gridf, 128, 0, st>>>(p, d_snv_row, d_snv_pos, d_snv_alt, n_snv, d_ref_max, d_alt_max,
+                                                       s->d_dual_list, (int)s->dual_motifs.size(), d_flags);
+        SMG_LAUNCH_CHECK("variant_windows_kernel(flagged)");
+        SMG_CUDA(cudaFreeAsync(d_flags, st));
+    }
+    if (!s->nondual_motifs.empty()) {
+        dim3 grid(nb, (unsigned)((s->nondual_motifs.size() + 31) / 32), 1);
+        variant_windows_kernel<<<grid, 128, 0, st>>>(p, d_snv_row, d_snv_pos, d_snv_alt, n_snv, d_ref_max, d_alt_max,
+                                                      s->d_nondual_list, (int)s->nondual_motifs.size(), nullptr);
+        SMG_LAUNCH_CHECK("variant_windows_kernel");
+    }
     return SMG_OK;
 }
-
 }  // extern "C"

@@ -346,3 +346,13 @@ def test_variant_windows_batched():
     e_ref, e_alt = so.variant_window_scan(seq, pos, alts, list(pw.weights))
     np.testing.assert_allclose(ref_max, e_ref, rtol=1e-5, atol=2e-5)
     np.testing.assert_allclose(alt_max, e_alt, rtol=1e-5, atol=2e-5)
+    # wide PWMs (generic kernel), IUPAC codes near the SNVs and an ambiguous alternate base (flagged -> generic kernel)
+    pw2 = synth_pwms(rng, 30, 3, 22)
+    seq2 = rand_seq(rng, 150) + "NNRYACGTN" + rand_seq(rng, 141)
+    pos2 = np.concatenate([np.arange(140, 170), rng.integers(0, 300, size=20)])
+    alts2 = ["ACGT"[rng.integers(0, 4)] for _ in pos2]
+    alts2[3] = "N"
+    r2, a2 = sb.variant.variant_window_scores([seq2], np.zeros(len(pos2), dtype=np.int32), pos2, alts2, pw2)
+    e2r, e2a = so.variant_window_scan(seq2, pos2, alts2, list(pw2.weights))
+    np.testing.assert_allclose(r2, e2r, rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(a2, e2a, rtol=1e-5, atol=2e-5)
