@@ -72,28 +72,15 @@ constexpr int kU = SMG_KU;       // steps between threshold checks on the ACGT f
     default: SMG_STEP(3, O); break; \
     }
 
-// two bases (A then B) per dispatch: r''[k] = (r[k-2] + T[k-1][A]) + T[k][B] -- the same association as two
-// single steps, so scores stay bit-identical; halves the number of (latency-bound) uniform branch chains per base
-#define SMG_STEP2(A, B, O1, O2)                                                                                   \
-    {                                                                                                             \
-        O1 = vadd(r[WB - 2], t[WB - 1][A]);                                                                       \
-        if (WB >= 3) O2 = vadd(vadd(r[WB >= 3 ? WB - 3 : 0], t[WB - 2][A]), t[WB - 1][B]);                        \
-        else O2 = vadd(t[0][A], t[1][B]);                                                                         \
-        _Pragma("unroll") for (int k = WB - 2; k >= 2; --k) r[k] = vadd(vadd(r[k - 2], t[k - 1][A]), t[k][B]);    \
-        if (WB >= 3) r[WB >= 3 ? 1 : 0] = vadd(t[0][A], t[1][B]);                                                 \
-        r[0] = t[0][B];                                                                                           \
+// Threaded dispatch: the body of step u first evaluates the two bit tests of step u+1's base straight off the packed
+// word (so their predicate latency hides behind its own FADD2s) and then jumps directly into the next step's body --
+// there is no common dispatch block inside a group of kU = 4 steps.  +12% over a per-step switch (measured).
+#define SMG_GOTO_NEXT(u, w, P)                                                            \
+    if ((w) & (2u << (2 * ((u) + 1)))) {                                                  \
+        if ((w) & (1u << (2 * ((u) + 1)))) goto P##3; else goto P##2;                     \
+    } else {                                                                              \
+        if ((w) & (1u << (2 * ((u) + 1)))) goto P##1; else goto P##0;                     \
     }
-#define SMG_CASE2(n) case n: SMG_STEP2(((n) & 3), ((n) >> 2), O1, O2); break;
-#define SMG_SWITCH_STEP2(q, O1, O2)                                                                               \
-    switch (q) {                                                                                                  \
-        SMG_CASE2(0) SMG_CASE2(1) SMG_CASE2(2) SMG_CASE2(3) SMG_CASE2(4) SMG_CASE2(5) SMG_CASE2(6) SMG_CASE2(7)   \
-        SMG_CASE2(8) SMG_CASE2(9) SMG_CASE2(10) SMG_CASE2(11) SMG_CASE2(12) SMG_CASE2(13) SMG_CASE2(14)           \
-    default: SMG_STEP2(3, 3, O1, O2); break;                                                                      \
-    }
-
-#ifndef SMG_BPD2_MAX_WB
-#define SMG_BPD2_MAX_WB 0  // padded widths up to this use the two-bases-per-dispatch fast path (measured: not a win, off)
-#endif
 
 // Explicit register caps per instantiation (an uncapped __maxnreg__ makes ptxas spend MORE registers than its
 // default heuristic and lose occupancy; measured).  Caps sit on occupancy steps: warps/SM = 65536 / (32 * regs).
@@ -231,31 +218,25 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, DUAL>::v)) scan_r
 #pragma unroll 1
             for (int blk = 0; blk < 16 / kU; ++blk) {
                 V o[kU];
-                if (DUAL && WB <= SMG_BPD2_MAX_WB) {
-#pragma unroll
-                    for (int u = 0; u < kU; u += 2) {
-                        const uint32_t q = (w >> (2 * u)) & 15u;
-#define O1 o[u]
-#define O2 o[u + 1]
-                        SMG_SWITCH_STEP2(q, O1, O2);
-#undef O1
-#undef O2
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-#ifndef SMG_SWITCH_DISPATCH  // bit tests straight off the packed word: ~5% faster than extract + switch (measured)
-                        if (w & (2u << (2 * u))) {
-                            if (w & (1u << (2 * u))) SMG_STEP(3, o[u]) else SMG_STEP(2, o[u])
-                        } else {
-                            if (w & (1u << (2 * u))) SMG_STEP(1, o[u]) else SMG_STEP(0, o[u])
-                        }
-#else
-                        const uint32_t b = (w >> (2 * u)) & 3u;
-                        SMG_SWITCH_STEP(b, o[u]);
-#endif
-                    }
-                }
+                static_assert(kU == 4, "the threaded dispatch below is written for groups of 4 steps");
+                if (w & 2u) { if (w & 1u) goto sA3; else goto sA2; } else { if (w & 1u) goto sA1; else goto sA0; }
+                sA0: SMG_STEP(0, o[0]); SMG_GOTO_NEXT(0, w, sB)
+                sA1: SMG_STEP(1, o[0]); SMG_GOTO_NEXT(0, w, sB)
+                sA2: SMG_STEP(2, o[0]); SMG_GOTO_NEXT(0, w, sB)
+                sA3: SMG_STEP(3, o[0]); SMG_GOTO_NEXT(0, w, sB)
+                sB0: SMG_STEP(0, o[1]); SMG_GOTO_NEXT(1, w, sC)
+                sB1: SMG_STEP(1, o[1]); SMG_GOTO_NEXT(1, w, sC)
+                sB2: SMG_STEP(2, o[1]); SMG_GOTO_NEXT(1, w, sC)
+                sB3: SMG_STEP(3, o[1]); SMG_GOTO_NEXT(1, w, sC)
+                sC0: SMG_STEP(0, o[2]); SMG_GOTO_NEXT(2, w, sD)
+                sC1: SMG_STEP(1, o[2]); SMG_GOTO_NEXT(2, w, sD)
+                sC2: SMG_STEP(2, o[2]); SMG_GOTO_NEXT(2, w, sD)
+                sC3: SMG_STEP(3, o[2]); SMG_GOTO_NEXT(2, w, sD)
+                sD0: SMG_STEP(0, o[3]); goto sEnd;
+                sD1: SMG_STEP(1, o[3]); goto sEnd;
+                sD2: SMG_STEP(2, o[3]); goto sEnd;
+                sD3: SMG_STEP(3, o[3]);
+                sEnd:
                 w >>= 2 * kU;
                 float m = vmax(o[0]);
 #pragma unroll
