@@ -50,7 +50,8 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe): one streaming
+    `nvidia-smi -lms 100` process, samples time-stamped on arrival; only those inside [t_start, t_end] are used."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -58,30 +59,40 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu_index, self.samples, self.stop_flag = gpu_index, [], False
+        self.gpu_index, self.samples, self.proc = gpu_index, [], None
+        self.t_start, self.t_end = None, None
 
     def run(self):
-        while not self.stop_flag:
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.samples.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.samples.append([x.strip() for x in line.split(",")])
+                self.proc.terminate()
             except Exception:
                 pass
-            time.sleep(0.1)
 
     def summary(self):
-        sm = [float(s[1]) for s in self.samples if len(s) > 8 and s[1].replace(".", "").isdigit()]
-        mx = [float(s[2]) for s in self.samples if len(s) > 8 and s[2].replace(".", "").isdigit()]
+        def isnum(x):
+            return x.replace(".", "", 1).isdigit()
+        inside = [s for t, s in self.samples if len(s) > 8 and (self.t_start is None or self.t_start <= t <= self.t_end)]
+        if not inside:  # region shorter than one sampling period: take the closest sample
+            inside = [s for t, s in self.samples if len(s) > 8][-1:]
+        sm = [float(s[1]) for s in inside if isnum(s[1])]
+        mx = [float(s[2]) for s in inside if isnum(s[2])]
+        pw = [float(s[3]) for s in inside if isnum(s[3])]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            if len(s) > 8:
-                for n, v in zip(names, s[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-        pw = [float(s[3]) for s in self.samples if len(s) > 8 and s[3].replace(".", "").isdigit()]
+        for s in inside:
+            for n, v in zip(names, s[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "power_w_max": max(pw) if pw else None, "samples": len(sm)}
 
@@ -125,7 +136,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=48, help="genomes in the bounded CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=120, help="genomes in the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -212,13 +223,14 @@ def main():
         if ev:
             ev[3].record()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.t_start = time.perf_counter()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     launches0 = _lib.launch_count()
     t_wall0 = time.perf_counter()
@@ -269,7 +281,8 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_t = float(tt.item())
     e2e_value = units * world / e2e_t / 1e9
-    sampler.stop_flag = True
+    sampler.t_end = time.perf_counter()
+    sampler.stop()
     sampler.join(timeout=2)
     clocks = sampler.summary()
 

@@ -356,3 +356,29 @@ def test_variant_windows_batched():
     e2r, e2a = so.variant_window_scan(seq2, pos2, alts2, list(pw2.weights))
     np.testing.assert_allclose(r2, e2r, rtol=1e-5, atol=2e-5)
     np.testing.assert_allclose(a2, e2a, rtol=1e-5, atol=2e-5)
+
+
+def test_benchmark_slice_full_parity_vs_c_oracle():
+    """BASELINE config c2 inputs (first 60 of the 1,000 genomes x all 1,000 PWMs, thr 0.7, both strands): the whole
+    count table, the hit count and an order-independent checksum of every hit key against the C oracle."""
+    sb = _sb()
+    from oracle import c_oracle
+    from smeagol_b200 import device as dev
+    from smeagol_b200 import synth
+
+    pw = synth.synth_pwms(1000, 7, 12)
+    genomes = synth.genome_set(1000, 10_000_000, 5000, 15000, seed=2)[:60]
+    model = sb.models.PWMModel(pw)
+    n = len(genomes)
+    out_rows = np.stack([2 * np.arange(n), 2 * np.arange(n) + 1], axis=1).astype(np.int32)
+    batch = dev.SeqBatch(genomes)
+    res = dev.scan(model.device_set, batch, model.thresholds(0.7), 3, out_rows, 2 * n)
+    lut = np.zeros(256, dtype=np.uint8)
+    lut[list(b"ACGT")] = [1, 2, 3, 4]
+    exp = c_oracle.scan([lut[g] for g in genomes], list(pw.weights), 0.7, strands=3, out_rows=out_rows, n_out_rows=2 * n)
+    assert (res.pos_bits, res.motif_bits) == (exp["pos_bits"], exp["motif_bits"])
+    np.testing.assert_array_equal(res.counts.cpu().numpy().astype(np.int64), exp["counts"])
+    assert res.n_hits == exp["n_hits"] and res.stats["n_hits_total"] == exp["n_hits"]
+    ksum, kxor = res.key_checksum()
+    assert ksum % (1 << 64) == exp["key_sum"] and kxor % (1 << 64) == exp["key_xor"]
+    assert res.stats["n_near"] >= exp["n_near"]  # the kernel's fp32 band is a superset of the oracle's fp64 band

@@ -141,3 +141,29 @@ def test_kernel_order_equals_ref_order_outside_band():
             np.testing.assert_array_equal(a[k], b[k])
         np.testing.assert_allclose(a["score"], b["score"], rtol=1e-5)
         np.testing.assert_array_equal(a["score64"].round(9), b["score64"].round(9))
+
+
+def test_c_oracle_equals_numpy_oracle():
+    """oracle/scan_oracle.c (the OpenMP restatement used for benchmark-sized parity) == oracle/scan_oracle.py."""
+    from oracle import c_oracle
+
+    rng = np.random.default_rng(3)
+    ws = [np.log2((rng.dirichlet([0.5] * 4, size=int(rng.integers(3, 25))) + 0.01) / 1.04 / 0.25) for _ in range(25)]
+    amb = "ACGTNWSMKRYBDHVZ"
+    pa = np.array([0.23] * 4 + [0.08 / 12] * 12)
+    seqs = ["".join(rng.choice(list("ACGT"), size=600)), "".join(rng.choice(list(amb), size=400, p=pa / pa.sum())), "ACGTA"]
+    codes = [so.integer_encode(s) for s in seqs]
+    for rcomp, strands in (("both", 3), ("none", 1), ("only", 2)):
+        exp = so.scan_rows(seqs, ws, 0.5, rcomp=rcomp, order="kernel")
+        n = len(seqs)
+        out_rows = {"both": np.stack([np.arange(n), n + np.arange(n)], 1), "none": np.stack([np.arange(n), np.zeros(n)], 1),
+                    "only": np.stack([np.zeros(n), np.arange(n)], 1)}[rcomp].astype(np.int32)
+        res = c_oracle.scan(codes, ws, 0.5, strands=strands, out_rows=out_rows, n_out_rows=2 * n, want_hits=True,
+                            hit_cap=200000)
+        pb, mb = res["pos_bits"], res["motif_bits"]
+        k = res["keys"]
+        np.testing.assert_array_equal((k >> np.uint64(pb + mb)).astype(np.int64), exp["row"])
+        np.testing.assert_array_equal(((k >> np.uint64(mb)) & np.uint64((1 << pb) - 1)).astype(np.int64), exp["pos"])
+        np.testing.assert_array_equal((k & np.uint64((1 << mb) - 1)).astype(np.int64), exp["motif"])
+        np.testing.assert_array_equal(res["scores"].view(np.uint32), exp["score"].view(np.uint32))
+        assert res["n_hits"] == len(exp["row"]) and res["counts"].sum() == len(exp["row"])
