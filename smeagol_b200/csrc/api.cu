@@ -71,7 +71,12 @@ struct smg_pwmset {
     int32_t* d_wide = nullptr;
 };
 
-static const int kDualMaxWidth = 16;
+#ifndef SMG_DUAL_MAX_WIDTH
+#define SMG_DUAL_MAX_WIDTH 32
+#endif
+// PWMs up to this width keep both strands in one lane (float2 pairs, half-swapped table); wider ones use one lane
+// per (PWM, strand) column
+static const int kDualMaxWidth = SMG_DUAL_MAX_WIDTH;
 
 // side streams used to run the per-width-bucket launches of one smg_scan call concurrently (per device)
 struct StreamPool {
@@ -448,13 +453,20 @@ int smg_pwmset_create(const float* h_weights, const int32_t* h_widths, int32_t n
             if (m < 0) continue;
             const int wm = h_widths[m];
             const float* T = h_weights + s->offs[m] * 4;
-            for (int k = 0; k < wm; ++k)
+            // forward tables are zero-padded at the tail; in DUAL groups the reverse-complement table
+            // Trc[k][b] = T[W-1-k][3-b] is padded at the HEAD, so that rc[k][b] == fwdpad[WB-1-k][3-b] for every k
+            // (the kernel keeps only half of the {fwd, rc} pairs and reads the others half-swapped)
+            for (int k = 0; k < g.wb; ++k)
                 for (int b = 0; b < 4; ++b) {
-                    const float fwd = T[k * 4 + b];
-                    const float rc = T[(wm - 1 - k) * 4 + (3 - b)];  // Trc[k][b] = T[W-1-k][3-b]
                     const size_t e = (size_t)(k * 4 + b) * 32 + l;
-                    if (g.dual) { gt[e * 2 + 0] = fwd; gt[e * 2 + 1] = rc; }
-                    else gt[e] = g.lane_strand[l] ? rc : fwd;
+                    const float fwd = k < wm ? T[k * 4 + b] : 0.f;
+                    if (g.dual) {
+                        const int kk = g.wb - 1 - k;
+                        gt[e * 2 + 0] = fwd;
+                        gt[e * 2 + 1] = kk < wm ? T[kk * 4 + (3 - b)] : 0.f;
+                    } else {
+                        gt[e] = k < wm ? (g.lane_strand[l] ? T[(wm - 1 - k) * 4 + (3 - b)] : fwd) : 0.f;
+                    }
                 }
         }
     }

@@ -48,6 +48,54 @@ __device__ __forceinline__ float vmix(const float e0, const float e1, const floa
     return smg_mix(e0, e1, e2, e3, t0, t1, t2, t3);
 }
 
+// Register-resident log-odds table of one lane.
+// DUAL lanes hold the pair P(k,b) = {T[k][b] (forward), Trc[k][b] (reverse complement)}.  With the RC table padded at
+// its HEAD (rows k < WB-W are zero) Trc[k][b] = T[WB-1-k][3-b] holds for every k, hence P(WB-1-k, 3-b) is P(k,b) with
+// its halves swapped -- and FADD2 takes a half-swapped operand for free (SASS operand modifier .F32x2.LO_HI).  Only
+// half of the pairs are kept: 4*WB registers instead of 8*WB, which is what buys the extra resident warps.
+template <int WB, bool DUAL> struct Tab;
+template <int WB> struct Tab<WB, false> {
+    float t[WB][4];
+    __device__ __forceinline__ void load(const float* __restrict__ gt, const int lane)
+    {
+#pragma unroll
+        for (int k = 0; k < WB; ++k)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) t[k][b] = gt[(k * 4 + b) * 32 + lane];
+    }
+    __device__ __forceinline__ float get(const int k, const int b) const { return t[k][b]; }
+};
+template <int WB> struct Tab<WB, true> {
+    static constexpr int H = WB / 2;
+    float2 h[H][4];
+    float2 hm[2];  // middle row (odd WB): bases A, C; G and T are their swapped partners
+    __device__ __forceinline__ void load(const float* __restrict__ gt_, const int lane)
+    {
+        const float2* gt = reinterpret_cast<const float2*>(gt_);
+#pragma unroll
+        for (int k = 0; k < H; ++k)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) h[k][b] = gt[(k * 4 + b) * 32 + lane];
+        if (WB & 1) {
+            hm[0] = gt[(H * 4 + 0) * 32 + lane];
+            hm[1] = gt[(H * 4 + 1) * 32 + lane];
+        } else {
+            hm[0] = hm[1] = make_float2(0.f, 0.f);
+        }
+    }
+    __device__ __forceinline__ float2 get(const int k, const int b) const
+    {
+        if (k < H) return h[k][b];
+        if (k >= WB - H) {
+            const float2 p = h[WB - 1 - k][3 - b];
+            return make_float2(p.y, p.x);
+        }
+        if (b < 2) return hm[b];
+        const float2 p = hm[3 - b];
+        return make_float2(p.y, p.x);
+    }
+};
+
 constexpr int kQCap = 16;        // per-lane candidate queue slots (a block of kU steps adds at most 2*kU)
 constexpr int kStageCap = 128;   // per-warp staged hits
 constexpr int kStageFlush = 64;  // flush when more than this many are staged (one event adds <= 32)
@@ -59,9 +107,9 @@ constexpr int kU = SMG_KU;       // steps between threshold checks on the ACGT f
 // one shift-register step for base B (compile-time); O receives the completed window score
 #define SMG_STEP(B, O)                                                                        \
     {                                                                                         \
-        O = vadd(r[WB - 2], t[WB - 1][B]);                                                    \
-        _Pragma("unroll") for (int k = WB - 2; k >= 1; --k) r[k] = vadd(r[k - 1], t[k][B]);   \
-        r[0] = t[0][B];                                                                       \
+        O = vadd(r[WB - 2], t.get(WB - 1, B));                                                \
+        _Pragma("unroll") for (int k = WB - 2; k >= 1; --k) r[k] = vadd(r[k - 1], t.get(k, B)); \
+        r[0] = t.get(0, B);                                                                   \
     }
 
 #define SMG_SWITCH_STEP(b, O)      \
@@ -85,8 +133,10 @@ constexpr int kU = SMG_KU;       // steps between threshold checks on the ACGT f
 // Explicit register caps per instantiation (an uncapped __maxnreg__ makes ptxas spend MORE registers than its
 // default heuristic and lose occupancy; measured).  Caps sit on occupancy steps: warps/SM = 65536 / (32 * regs).
 template <int WB, bool DUAL> struct MaxRegs {
-    static constexpr int v = DUAL ? (WB <= 9 ? 128 : WB == 10 ? 144 : WB <= 13 ? 168 : WB == 14 ? 216 : WB == 15 ? 224 : 240)
-                                  : (WB <= 19 ? 144 : WB <= 26 ? 168 : 240);
+#ifndef SMG_REGCAPS
+#define SMG_REGCAPS(WB) ((WB) <= 8 ? 80 : (WB) <= 10 ? 96 : (WB) <= 12 ? 104 : (WB) == 13 ? 112 : (WB) <= 16 ? 128 : (WB) <= 20 ? 168 : (WB) <= 24 ? 192 : 240)
+#endif
+    static constexpr int v = DUAL ? SMG_REGCAPS(WB) : (WB <= 19 ? 144 : WB <= 26 ? 168 : 240);
 };
 
 template <int WB, bool DUAL>
@@ -105,18 +155,13 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, DUAL>::v)) scan_r
     const smg_row_t row = p.rows[ch.row];
 
     // ---- per-lane PWM: table into registers, thresholds, trim bound
-    V t[WB][4];
-    {
-        const V* gt = reinterpret_cast<const V*>(p.group_tab + p.group_tab_off[group]);
-#pragma unroll
-        for (int k = 0; k < WB; ++k)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) t[k][b] = gt[(k * 4 + b) * 32 + lane];
-    }
+    Tab<WB, DUAL> t;
+    t.load(p.group_tab + p.group_tab_off[group], lane);
     const int motif = p.lane_motif[group * 32 + lane];
     const int my_strand = DUAL ? 0 : p.lane_strand[group * 32 + lane];
     const bool active = motif >= 0 && (DUAL || ((p.strands >> my_strand) & 1));
     const int wm = motif >= 0 ? p.motif_width[motif] : 0;
+    const int rc_shift = DUAL ? (WB - (motif >= 0 ? wm : WB)) : 0;  // RC table is head-padded: its window starts later
     const float thr_lo = active ? p.thr_lo[motif] : __int_as_float(0x7f800000);
     const float thr_hi = active ? p.thr_hi[motif] : __int_as_float(0x7f800000);
     const long long smax64 = row.g_len - row.g_off - (long long)wm;  // largest window start that fits (row-local)
@@ -173,7 +218,7 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, DUAL>::v)) scan_r
             const uint2 e = have ? s_q[j][lane] : make_uint2(0u, 0u);
             const float v = __uint_as_float(e.y);
             const int st = DUAL ? (int)(e.x & 1u) : my_strand;
-            const int s = s_origin + (int)(e.x >> 1);
+            const int s = s_origin + (int)(e.x >> 1) + (st ? rc_shift : 0);
             const bool cand = have && (s >= c0) && (s < c1) && (s <= smax) && (DUAL ? ((p.strands >> st) & 1) : true);
             const bool hit = cand && (v > thr_hi);
             if (hit) {
@@ -265,11 +310,11 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, DUAL>::v)) scan_r
                     const int q = s_base + (WB - 1) + j;  // row-local position of this base
                     const int code = (cp != nullptr && q < row.n_avail) ? (int)cp[q] : 0;
                     const float e0 = c_emb[code][0], e1 = c_emb[code][1], e2 = c_emb[code][2], e3 = c_emb[code][3];
-                    o = vadd(r[WB - 2], vmix(e0, e1, e2, e3, t[WB - 1][0], t[WB - 1][1], t[WB - 1][2], t[WB - 1][3]));
+                    o = vadd(r[WB - 2], vmix(e0, e1, e2, e3, t.get(WB - 1, 0), t.get(WB - 1, 1), t.get(WB - 1, 2), t.get(WB - 1, 3)));
 #pragma unroll
                     for (int k = WB - 2; k >= 1; --k)
-                        r[k] = vadd(r[k - 1], vmix(e0, e1, e2, e3, t[k][0], t[k][1], t[k][2], t[k][3]));
-                    r[0] = vmix(e0, e1, e2, e3, t[0][0], t[0][1], t[0][2], t[0][3]);
+                        r[k] = vadd(r[k - 1], vmix(e0, e1, e2, e3, t.get(k, 0), t.get(k, 1), t.get(k, 2), t.get(k, 3)));
+                    r[0] = vmix(e0, e1, e2, e3, t.get(0, 0), t.get(0, 1), t.get(0, 2), t.get(0, 3));
                 }
                 if (__any_sync(SMG_FULL_MASK, vmax(o) > thr_lo)) {
                     if (vget(o, 0) > thr_lo) push(vget(o, 0), wi * 16 + j, 0);

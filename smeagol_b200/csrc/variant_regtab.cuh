@@ -28,16 +28,11 @@ __global__ void __launch_bounds__(32) variant_regtab_kernel(const VariantParams 
     const ScanParams& p = vp.sp;
     const int lane = threadIdx.x;
     const int group = p.first_group + blockIdx.y;
-    V t[WB][4];
-    {
-        const V* gt = reinterpret_cast<const V*>(p.group_tab + p.group_tab_off[group]);
-#pragma unroll
-        for (int k = 0; k < WB; ++k)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) t[k][b] = gt[(k * 4 + b) * 32 + lane];
-    }
+    Tab<WB, true> t;
+    t.load(p.group_tab + p.group_tab_off[group], lane);
     const int motif = p.lane_motif[group * 32 + lane];
     const int wm = motif >= 0 ? p.motif_width[motif] : 1;
+    const int rc_shift = WB - (motif >= 0 ? wm : WB);  // head-padded RC table: its window completes rc_shift steps earlier
     const float ninf = __int_as_float(0xff800000);
     constexpr int NSTEP = 2 * WB - 1;
 
@@ -118,7 +113,8 @@ __global__ void __launch_bounds__(32) variant_regtab_kernel(const VariantParams 
                 }
                 L0 = (L0 >> 2) | (H0 << 62);
                 H0 >>= 2;
-                if (i >= imin && i <= imax) mx = vmax3(mx, o);
+                if (i >= imin && i <= imax) mx = fmaxf(mx, o.x);
+                if (i >= imin - rc_shift && i <= imax - rc_shift) mx = fmaxf(mx, o.y);
             }
             res[pass] = mx;
         }

@@ -41,7 +41,8 @@ for W in widths:
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     lookups = L * 2.0 * W * nm
-    print("W=%2d  %7.3f ms  %6.2f T lookup-add/s  %5.1f%% of FP32 peak  %6.1f Gbase*motif/s  hit density %.2e" % (
-        W, best, lookups / best / 1e9, lookups / best / 1e9 / 36.9 * 100, L * nm / best / 1e6,
+    print("W=%2d groups=%d buckets=%d  %7.3f ms  %6.2f T lookup-add/s  %5.1f%% of FP32 peak  %6.1f Gbase*motif/s  hit density %.2e" % (
+        W, model.device_set.n_groups, model.device_set.n_buckets,
+        best, lookups / best / 1e9, lookups / best / 1e9 / 36.9 * 100, L * nm / best / 1e6,
         res.stats["n_hits_total"] / (2.0 * L * nm)), flush=True)
     model.device_set.close()
