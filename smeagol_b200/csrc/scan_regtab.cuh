@@ -131,10 +131,12 @@ constexpr int kU = SMG_KU;       // steps between threshold checks on the ACGT f
     }
 
 // Explicit register caps per instantiation (an uncapped __maxnreg__ makes ptxas spend MORE registers than its
-// default heuristic and lose occupancy; measured).  Caps sit on occupancy steps: warps/SM = 65536 / (32 * regs).
+// default heuristic and lose occupancy; measured).  Registers are partitioned per SM sub-partition (16K each), so
+// the occupancy steps are 64/72/80/96/128/168 registers = 8/7/6/5/4/3 one-warp CTAs per sub-partition; the caps
+// below are the measured best step for each width (tools/bench_widths.py).
 template <int WB, bool DUAL> struct MaxRegs {
 #ifndef SMG_REGCAPS
-#define SMG_REGCAPS(WB) ((WB) <= 8 ? 80 : (WB) <= 10 ? 96 : (WB) <= 12 ? 104 : (WB) == 13 ? 112 : (WB) <= 16 ? 128 : (WB) <= 20 ? 168 : (WB) <= 24 ? 192 : 240)
+#define SMG_REGCAPS(WB) ((WB) <= 6 ? 72 : (WB) <= 8 ? 80 : (WB) <= 10 ? 96 : (WB) <= 12 ? 104 : (WB) <= 16 ? 128 : (WB) <= 24 ? 168 : 240)
 #endif
     static constexpr int v = DUAL ? SMG_REGCAPS(WB) : (WB <= 19 ? 144 : WB <= 26 ? 168 : 240);
 };
