@@ -37,15 +37,14 @@ static int fail(int code, const std::string& msg)
     } while (0)
 
 struct Group {
-    int wb;
-    bool dual;
-    int lane_motif[32];
-    int lane_strand[32];
+    int wb;  // padded width
+    int nm;  // PWMs per lane (1 or 2)
+    int lane_motif[SMG_MAX_PWMS_PER_LANE][32];
     int64_t tab_off;
 };
 struct Bucket {
     int wb;
-    bool dual;
+    int nm;
     int first_group;
     int n_groups;
 };
@@ -67,7 +66,6 @@ struct smg_pwmset {
     float* d_gtab = nullptr;
     int64_t* d_gtab_off = nullptr;
     int32_t* d_lane_motif = nullptr;
-    int32_t* d_lane_strand = nullptr;
     int32_t* d_wide = nullptr;
 };
 
@@ -77,6 +75,10 @@ struct smg_pwmset {
 // PWMs up to this width keep both strands in one lane (float2 pairs, half-swapped table); wider ones use one lane
 // per (PWM, strand) column
 static const int kDualMaxWidth = SMG_DUAL_MAX_WIDTH;
+#ifndef SMG_PAIR_MAX_WIDTH
+#define SMG_PAIR_MAX_WIDTH 0  // measured: two PWMs per lane lose more occupancy than they save in dispatch (off)
+#endif
+static const int kPairMaxWidth = SMG_PAIR_MAX_WIDTH;  // lanes hold two PWMs up to this (padded) width
 
 // side streams used to run the per-width-bucket launches of one smg_scan call concurrently (per device)
 struct StreamPool {
@@ -395,79 +397,74 @@ int smg_pwmset_create(const float* h_weights, const int32_t* h_widths, int32_t n
     for (int64_t i = 0; i < tot * 4; ++i)
         if (!std::isfinite(h_weights[i])) { delete s; return fail(SMG_ERR_INVALID, "smg_pwmset_create: non-finite PWM weight"); }
 
-    // ---- lane groups: columns sorted by width, 32 per group, remainders carried up to the next width
-    struct Col { int motif, strand; };
-    auto build = [&](bool dual, int wlo, int whi) {
-        std::vector<Col> pool;
-        auto emit_group = [&](int wb, size_t n_take) {
+    // ---- lane groups: PWMs sorted by width; a lane holds NM = 2 PWMs while 2 * width <= 2 * kPairMaxWidth (more adds
+    // per uniform branch), else 1; 32 * NM PWMs per group; remainders are carried up to the next width (zero padding)
+    {
+        std::vector<int> pool;
+        auto emit_group = [&](int wb, int nm, size_t n_take) {
             Group g;
             g.wb = std::max(wb, 2);
-            g.dual = dual;
+            g.nm = nm;
             g.tab_off = 0;
-            for (int l = 0; l < 32; ++l) { g.lane_motif[l] = -1; g.lane_strand[l] = 0; }
-            for (size_t l = 0; l < n_take; ++l) { g.lane_motif[l] = pool[l].motif; g.lane_strand[l] = pool[l].strand; }
+            for (int m = 0; m < SMG_MAX_PWMS_PER_LANE; ++m)
+                for (int l = 0; l < 32; ++l) g.lane_motif[m][l] = -1;
+            for (size_t i = 0; i < n_take; ++i) g.lane_motif[i / 32][i % 32] = pool[i];
             pool.erase(pool.begin(), pool.begin() + n_take);
             s->groups.push_back(g);
         };
         int last_w = 0;
-        for (int w = wlo; w <= whi; ++w) {
+        for (int w = 1; w <= kDualMaxWidth; ++w) {
             bool any = false;
-            for (int m = 0; m < n_motifs; ++m) {
-                if (h_widths[m] != w) continue;
-                any = true;
-                if (dual) pool.push_back({m, 0});
-                else { pool.push_back({m, 0}); pool.push_back({m, 1}); }
-            }
+            for (int m = 0; m < n_motifs; ++m)
+                if (h_widths[m] == w) { pool.push_back(m); any = true; }
             if (any) last_w = w;
-            while (pool.size() >= 32) emit_group(w, 32);
+            const int nm = (std::max(w, 2) <= kPairMaxWidth) ? 2 : 1;
+            while (pool.size() >= (size_t)32 * nm) emit_group(w, nm, (size_t)32 * nm);
         }
-        if (!pool.empty()) emit_group(last_w, pool.size());
-    };
-    build(true, 1, kDualMaxWidth);
-    build(false, kDualMaxWidth + 1, SMG_MAX_REGTAB_WIDTH);
+        while (!pool.empty()) {
+            const int nm = (std::max(last_w, 2) <= kPairMaxWidth && pool.size() > 32) ? 2 : 1;
+            emit_group(last_w, nm, std::min(pool.size(), (size_t)32 * nm));
+        }
+    }
     for (int m = 0; m < n_motifs; ++m)
         if (h_widths[m] > SMG_MAX_REGTAB_WIDTH) s->wide.push_back(m);
-    // buckets of equal (wb, dual), groups reordered so that a bucket is contiguous
+    // buckets of equal (wb, nm), groups reordered so that a bucket is contiguous
     std::stable_sort(s->groups.begin(), s->groups.end(), [](const Group& a, const Group& b) {
-        if (a.dual != b.dual) return a.dual > b.dual;
+        if (a.nm != b.nm) return a.nm > b.nm;
         return a.wb < b.wb;
     });
     std::vector<float> gtab;
     std::vector<int64_t> gtab_off;
-    std::vector<int32_t> lane_motif, lane_strand;
+    std::vector<int32_t> lane_motif;
     for (size_t gi = 0; gi < s->groups.size(); ++gi) {
         Group& g = s->groups[gi];
-        if (s->buckets.empty() || s->buckets.back().wb != g.wb || s->buckets.back().dual != g.dual)
-            s->buckets.push_back({g.wb, g.dual, (int)gi, 0});
+        if (s->buckets.empty() || s->buckets.back().wb != g.wb || s->buckets.back().nm != g.nm)
+            s->buckets.push_back({g.wb, g.nm, (int)gi, 0});
         s->buckets.back().n_groups++;
         g.tab_off = (int64_t)gtab.size();
         gtab_off.push_back(g.tab_off);
-        const int comps = g.dual ? 2 : 1;
-        gtab.resize(gtab.size() + (size_t)g.wb * 4 * 32 * comps, 0.f);
-        float* gt = gtab.data() + g.tab_off;
-        s->sum_padded += (int64_t)g.wb * comps;
-        for (int l = 0; l < 32; ++l) {
-            lane_motif.push_back(g.lane_motif[l]);
-            lane_strand.push_back(g.lane_strand[l]);
-            const int m = g.lane_motif[l];
-            if (m < 0) continue;
-            const int wm = h_widths[m];
-            const float* T = h_weights + s->offs[m] * 4;
-            // forward tables are zero-padded at the tail; in DUAL groups the reverse-complement table
-            // Trc[k][b] = T[W-1-k][3-b] is padded at the HEAD, so that rc[k][b] == fwdpad[WB-1-k][3-b] for every k
-            // (the kernel keeps only half of the {fwd, rc} pairs and reads the others half-swapped)
-            for (int k = 0; k < g.wb; ++k)
-                for (int b = 0; b < 4; ++b) {
-                    const size_t e = (size_t)(k * 4 + b) * 32 + l;
-                    const float fwd = k < wm ? T[k * 4 + b] : 0.f;
-                    if (g.dual) {
+        const size_t slot_floats = (size_t)g.wb * 4 * 32 * 2;
+        gtab.resize(gtab.size() + slot_floats * g.nm, 0.f);
+        s->sum_padded += (int64_t)g.wb * 2 * g.nm;
+        for (int sm = 0; sm < SMG_MAX_PWMS_PER_LANE; ++sm) {
+            for (int l = 0; l < 32; ++l) {
+                const int m = g.lane_motif[sm][l];
+                lane_motif.push_back(m);
+                if (m < 0 || sm >= g.nm) continue;
+                float* gt = gtab.data() + g.tab_off + slot_floats * sm;
+                const int wm = h_widths[m];
+                const float* T = h_weights + s->offs[m] * 4;
+                // the forward table is zero-padded at the tail, the reverse-complement table
+                // Trc[k][b] = T[W-1-k][3-b] at the HEAD, so that rc[k][b] == fwdpad[WB-1-k][3-b] for every k (the
+                // kernel keeps only half of the {fwd, rc} pairs and reads the others half-swapped)
+                for (int k = 0; k < g.wb; ++k)
+                    for (int b = 0; b < 4; ++b) {
+                        const size_t e = (size_t)(k * 4 + b) * 32 + l;
                         const int kk = g.wb - 1 - k;
-                        gt[e * 2 + 0] = fwd;
+                        gt[e * 2 + 0] = k < wm ? T[k * 4 + b] : 0.f;
                         gt[e * 2 + 1] = kk < wm ? T[kk * 4 + (3 - b)] : 0.f;
-                    } else {
-                        gt[e] = k < wm ? (g.lane_strand[l] ? T[(wm - 1 - k) * 4 + (3 - b)] : fwd) : 0.f;
                     }
-                }
+            }
         }
     }
     std::vector<float> nat(h_weights, h_weights + tot * 4);
@@ -477,7 +474,7 @@ int smg_pwmset_create(const float* h_weights, const int32_t* h_widths, int32_t n
     std::vector<int32_t> dualv(s->dual_motifs.begin(), s->dual_motifs.end()), nondualv(s->nondual_motifs.begin(), s->nondual_motifs.end());
     if ((rc = upload(&s->d_nat, nat)) || (rc = upload(&s->d_width, wv)) || (rc = upload(&s->d_off, s->offs)) ||
         (rc = upload(&s->d_gtab, gtab)) || (rc = upload(&s->d_gtab_off, gtab_off)) ||
-        (rc = upload(&s->d_lane_motif, lane_motif)) || (rc = upload(&s->d_lane_strand, lane_strand)) ||
+        (rc = upload(&s->d_lane_motif, lane_motif)) ||
         (rc = upload(&s->d_wide, widev)) || (rc = upload(&s->d_dual_list, dualv)) || (rc = upload(&s->d_nondual_list, nondualv))) {
         smg_pwmset_destroy(s);
         return rc;
@@ -490,7 +487,7 @@ int smg_pwmset_destroy(smg_pwmset_t s)
 {
     if (!s) return SMG_OK;
     cudaFree(s->d_nat); cudaFree(s->d_width); cudaFree(s->d_off); cudaFree(s->d_gtab); cudaFree(s->d_gtab_off);
-    cudaFree(s->d_lane_motif); cudaFree(s->d_lane_strand); cudaFree(s->d_wide); cudaFree(s->d_dual_list); cudaFree(s->d_nondual_list);
+    cudaFree(s->d_lane_motif); cudaFree(s->d_wide); cudaFree(s->d_dual_list); cudaFree(s->d_nondual_list);
     delete s;
     return SMG_OK;
 }
@@ -525,7 +522,7 @@ static void fill_params(ScanParams& p, smg_pwmset_t s, const uint32_t* d_packed,
     memset(&p, 0, sizeof(p));
     p.packed = d_packed; p.amask = d_amask; p.codes = d_codes; p.rows = d_rows; p.out_rows = d_out_rows;
     p.n_motifs = s->n_motifs; p.motif_width = s->d_width; p.motif_off = s->d_off; p.nat_tab = s->d_nat;
-    p.group_tab = s->d_gtab; p.group_tab_off = s->d_gtab_off; p.lane_motif = s->d_lane_motif; p.lane_strand = s->d_lane_strand;
+    p.group_tab = s->d_gtab; p.group_tab_off = s->d_gtab_off; p.lane_motif = s->d_lane_motif;
 }
 
 int smg_scan(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes, const smg_row_t* d_rows,
@@ -557,7 +554,7 @@ int smg_scan(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amask, 
     SMG_CUDA(cudaEventRecord(pool->fork, st));
     int bi = 0;
     for (const Bucket& b : s->buckets) {
-        smg_launch_fn fn = smg_get_launcher(b.wb, b.dual);
+        smg_launch_fn fn = smg_get_launcher(b.wb, b.nm);
         if (!fn) return fail(SMG_ERR_INVALID, "smg_scan: no kernel for padded width " + std::to_string(b.wb));
         cudaStream_t bs = (bi == 0) ? st : pool->side[(bi - 1) % StreamPool::kSide];
         if (bi > 0 && bi <= StreamPool::kSide) SMG_CUDA(cudaStreamWaitEvent(bs, pool->fork, 0));
@@ -667,11 +664,10 @@ int smg_variant_windows(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t
         vp.ref_max = d_ref_max; vp.alt_max = d_alt_max; vp.slow_flags = d_flags;
         const int blocks = (int)std::min<int64_t>(n_snv, 148 * 16 * 4);
         for (const Bucket& b : s->buckets) {
-            if (!b.dual) continue;
             smg_variant_launch_fn fn = smg_get_variant_launcher(b.wb);
             if (!fn) return fail(SMG_ERR_INVALID, "smg_variant_windows: no kernel for padded width " + std::to_string(b.wb));
             vp.sp.first_group = b.first_group;
-            fn(vp, blocks, b.n_groups, st);
+            fn(vp, blocks, b.n_groups, b.nm, st);
             SMG_LAUNCH_CHECK("variant_regtab_kernel");
         }
         dim3 gridf(nb, (unsigned)((s->dual_motifs.size() + 31) / 32), 1);

@@ -6,6 +6,7 @@
 #include "../../include/smeagol_b200.h"
 
 #define SMG_FULL_MASK 0xffffffffu
+#define SMG_MAX_PWMS_PER_LANE 2  // a lane of the register-table kernels holds 1 or 2 PWMs (both strands each)
 
 // 17 x 4 soft one-hot table of the reference alphabet Z,A,C,G,T,U,N,W,S,M,K,R,Y,B,D,H,V
 // (smeagol/encode.py:11-29), fp32 as the reference's Embedding layer holds it (models.py:89).
@@ -87,7 +88,6 @@ struct ScanParams {
     const float* nat_tab;         // [sum W][4]
     const float* group_tab;       // lane-major register tables of all groups
     const int64_t* group_tab_off; // [n_groups] offset (in floats) of each group's table
-    const int32_t* lane_motif;    // [n_groups][32], -1 = empty lane
-    const int32_t* lane_strand;   // [n_groups][32], single-strand groups only
+    const int32_t* lane_motif;    // [n_groups][SMG_MAX_PWMS_PER_LANE][32], -1 = empty slot
     int32_t first_group;          // first group of the bucket being launched
 };

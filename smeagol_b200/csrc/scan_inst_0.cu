@@ -1,16 +1,15 @@
-// Explicit instantiations of the fused scan kernel (part 0): both strands per lane, padded widths 2..8.
+// Explicit instantiations of the fused scan kernel (part 0).
 #include "scan_regtab.cuh"
 #include "launchers.h"
 
-smg_launch_fn smg_get_launcher_part0(int wb, bool dual)
+smg_launch_fn smg_get_launcher_part0(int wb, int nm)
 {
-    if (!dual) return nullptr;  // one-strand-per-lane groups are not built any more (see api.cu)
-    if (wb == 2) return &smg::launch_scan_regtab<2, true>;
-    if (wb == 3) return &smg::launch_scan_regtab<3, true>;
-    if (wb == 4) return &smg::launch_scan_regtab<4, true>;
-    if (wb == 5) return &smg::launch_scan_regtab<5, true>;
-    if (wb == 6) return &smg::launch_scan_regtab<6, true>;
-    if (wb == 7) return &smg::launch_scan_regtab<7, true>;
-    if (wb == 8) return &smg::launch_scan_regtab<8, true>;
+    if (wb == 2 && nm == 1) return &smg::launch_scan_regtab<2, 1>;
+    if (wb == 3 && nm == 1) return &smg::launch_scan_regtab<3, 1>;
+    if (wb == 4 && nm == 1) return &smg::launch_scan_regtab<4, 1>;
+    if (wb == 5 && nm == 1) return &smg::launch_scan_regtab<5, 1>;
+    if (wb == 6 && nm == 1) return &smg::launch_scan_regtab<6, 1>;
+    if (wb == 7 && nm == 1) return &smg::launch_scan_regtab<7, 1>;
+    if (wb == 8 && nm == 1) return &smg::launch_scan_regtab<8, 1>;
     return nullptr;
 }

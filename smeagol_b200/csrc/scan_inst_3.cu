@@ -1,14 +1,13 @@
-// Explicit instantiations of the fused scan kernel (part 3): both strands per lane, padded widths 17..21.
+// Explicit instantiations of the fused scan kernel (part 3).
 #include "scan_regtab.cuh"
 #include "launchers.h"
 
-smg_launch_fn smg_get_launcher_part3(int wb, bool dual)
+smg_launch_fn smg_get_launcher_part3(int wb, int nm)
 {
-    if (!dual) return nullptr;  // one-strand-per-lane groups are not built any more (see api.cu)
-    if (wb == 17) return &smg::launch_scan_regtab<17, true>;
-    if (wb == 18) return &smg::launch_scan_regtab<18, true>;
-    if (wb == 19) return &smg::launch_scan_regtab<19, true>;
-    if (wb == 20) return &smg::launch_scan_regtab<20, true>;
-    if (wb == 21) return &smg::launch_scan_regtab<21, true>;
+    if (wb == 17 && nm == 1) return &smg::launch_scan_regtab<17, 1>;
+    if (wb == 18 && nm == 1) return &smg::launch_scan_regtab<18, 1>;
+    if (wb == 19 && nm == 1) return &smg::launch_scan_regtab<19, 1>;
+    if (wb == 20 && nm == 1) return &smg::launch_scan_regtab<20, 1>;
+    if (wb == 21 && nm == 1) return &smg::launch_scan_regtab<21, 1>;
     return nullptr;
 }

@@ -1,14 +1,13 @@
-// Explicit instantiations of the fused scan kernel (part 4): both strands per lane, padded widths 22..26.
+// Explicit instantiations of the fused scan kernel (part 4).
 #include "scan_regtab.cuh"
 #include "launchers.h"
 
-smg_launch_fn smg_get_launcher_part4(int wb, bool dual)
+smg_launch_fn smg_get_launcher_part4(int wb, int nm)
 {
-    if (!dual) return nullptr;  // one-strand-per-lane groups are not built any more (see api.cu)
-    if (wb == 22) return &smg::launch_scan_regtab<22, true>;
-    if (wb == 23) return &smg::launch_scan_regtab<23, true>;
-    if (wb == 24) return &smg::launch_scan_regtab<24, true>;
-    if (wb == 25) return &smg::launch_scan_regtab<25, true>;
-    if (wb == 26) return &smg::launch_scan_regtab<26, true>;
+    if (wb == 22 && nm == 1) return &smg::launch_scan_regtab<22, 1>;
+    if (wb == 23 && nm == 1) return &smg::launch_scan_regtab<23, 1>;
+    if (wb == 24 && nm == 1) return &smg::launch_scan_regtab<24, 1>;
+    if (wb == 25 && nm == 1) return &smg::launch_scan_regtab<25, 1>;
+    if (wb == 26 && nm == 1) return &smg::launch_scan_regtab<26, 1>;
     return nullptr;
 }

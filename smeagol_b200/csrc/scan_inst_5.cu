@@ -1,15 +1,14 @@
-// Explicit instantiations of the fused scan kernel (part 5): both strands per lane, padded widths 27..32.
+// Explicit instantiations of the fused scan kernel (part 5).
 #include "scan_regtab.cuh"
 #include "launchers.h"
 
-smg_launch_fn smg_get_launcher_part5(int wb, bool dual)
+smg_launch_fn smg_get_launcher_part5(int wb, int nm)
 {
-    if (!dual) return nullptr;  // one-strand-per-lane groups are not built any more (see api.cu)
-    if (wb == 27) return &smg::launch_scan_regtab<27, true>;
-    if (wb == 28) return &smg::launch_scan_regtab<28, true>;
-    if (wb == 29) return &smg::launch_scan_regtab<29, true>;
-    if (wb == 30) return &smg::launch_scan_regtab<30, true>;
-    if (wb == 31) return &smg::launch_scan_regtab<31, true>;
-    if (wb == 32) return &smg::launch_scan_regtab<32, true>;
+    if (wb == 27 && nm == 1) return &smg::launch_scan_regtab<27, 1>;
+    if (wb == 28 && nm == 1) return &smg::launch_scan_regtab<28, 1>;
+    if (wb == 29 && nm == 1) return &smg::launch_scan_regtab<29, 1>;
+    if (wb == 30 && nm == 1) return &smg::launch_scan_regtab<30, 1>;
+    if (wb == 31 && nm == 1) return &smg::launch_scan_regtab<31, 1>;
+    if (wb == 32 && nm == 1) return &smg::launch_scan_regtab<32, 1>;
     return nullptr;
 }

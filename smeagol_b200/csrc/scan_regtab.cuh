@@ -3,69 +3,43 @@
 // Replaces PWMModel.predict + np.where threshold + end trim (smeagol/models.py:92-117) and the per-(row, motif,
 // strand) counting of scan._count_sites (smeagol/scan.py:114-147) for both strands in ONE pass.
 //
-// Mapping (B200-first, not a Conv1D): one warp per CTA; every LANE owns one PWM (both strands, as the two halves
-// of a float2) or one (PWM, strand) column, with its whole log-odds table in REGISTERS.  The sequence is the
-// warp-uniform operand: all lanes consume the same base at the same step, so the table row is selected by
-// uniform control flow (4-way branch on the 2-bit base) and no per-lane indexing, shared-memory lookup or bank
-// conflict exists.  The window sum is a shift register:  r[k] <- r[k-1] + T[k][b]  (ascending-k summation order,
-// bit-identical to a sequential fp32 sum), advanced with packed FADD2 (sm_100 fp32x2) so that one issue slot
-// performs the add for the forward AND the reverse-complement strand (RC strand = forward string scanned with
-// Trc[k][b] = T[W-1-k][3-b]).  Completed window scores are checked against the per-PWM threshold every U steps;
-// hits are compacted with warp ballot + prefix popcount into a per-warp shared-memory stage and appended to the
-// global hit list with one atomic per flush; per-lane counters give the count table.
+// Mapping (B200-first, not a Conv1D): one warp per CTA; every LANE owns NM (1 or 2) PWMs, both strands each, with the
+// log-odds tables in REGISTERS.  The sequence is the warp-uniform operand: all lanes consume the same base at the same
+// step, so the table row is selected by uniform control flow (bit tests on the packed word) and no per-lane
+// indexing, shared-memory lookup or bank conflict exists.  The window sum is a shift register
+// r[k] <- r[k-1] + T[k][b]  (ascending-k summation order, bit-identical to a sequential fp32 sum), advanced with
+// packed FADD2 (sm_100 fp32x2): one issue slot performs the add for the forward AND the reverse-complement strand
+// (RC strand = forward string scanned with Trc[k][b] = T[W-1-k][3-b]).  Completed window scores are checked against
+// the per-PWM threshold every 4 steps; candidates go to per-lane queues in shared memory and are drained with warp
+// ballot + prefix popcount into a per-warp stage that is appended to the global hit list with one atomic per flush;
+// per-lane counters give the count table.
 //
 // Algorithmic work: 2*W lookup-adds per base x motif (both strands).  The binding unit is the FP32 pipe
-// (128 lanes/clk/SM; FADD2 issues 64 adds per slot), not shared memory: measured ~2x the LDS gather roofline.
+// (128 lanes/clk/SM; FADD2 issues 64 adds per slot), not shared memory.
 #pragma once
 #include "common.cuh"
 
 namespace smg {
 
-template <bool DUAL> struct VecOf { using T = float2; };
-template <> struct VecOf<false> { using T = float; };
-
 __device__ __forceinline__ float2 vadd(const float2 a, const float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float vadd(const float a, const float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ float vmax(const float2 a) { return fmaxf(a.x, a.y); }
-__device__ __forceinline__ float vmax(const float a) { return a; }
 __device__ __forceinline__ float vmax3(const float m, const float2 a)
 {
     float d;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(m), "f"(a.x), "f"(a.y));
     return d;
 }
-__device__ __forceinline__ float vmax3(const float m, const float a) { return fmaxf(m, a); }
-__device__ __forceinline__ float vget(const float2 a, const int s) { return s ? a.y : a.x; }
-__device__ __forceinline__ float vget(const float a, const int) { return a; }
 __device__ __forceinline__ float2 vmix(const float e0, const float e1, const float e2, const float e3, const float2 t0,
                                        const float2 t1, const float2 t2, const float2 t3)
 {
     return make_float2(smg_mix(e0, e1, e2, e3, t0.x, t1.x, t2.x, t3.x), smg_mix(e0, e1, e2, e3, t0.y, t1.y, t2.y, t3.y));
 }
-__device__ __forceinline__ float vmix(const float e0, const float e1, const float e2, const float e3, const float t0,
-                                      const float t1, const float t2, const float t3)
-{
-    return smg_mix(e0, e1, e2, e3, t0, t1, t2, t3);
-}
 
-// Register-resident log-odds table of one lane.
-// DUAL lanes hold the pair P(k,b) = {T[k][b] (forward), Trc[k][b] (reverse complement)}.  With the RC table padded at
-// its HEAD (rows k < WB-W are zero) Trc[k][b] = T[WB-1-k][3-b] holds for every k, hence P(WB-1-k, 3-b) is P(k,b) with
-// its halves swapped -- and FADD2 takes a half-swapped operand for free (SASS operand modifier .F32x2.LO_HI).  Only
-// half of the pairs are kept: 4*WB registers instead of 8*WB, which is what buys the extra resident warps.
-template <int WB, bool DUAL> struct Tab;
-template <int WB> struct Tab<WB, false> {
-    float t[WB][4];
-    __device__ __forceinline__ void load(const float* __restrict__ gt, const int lane)
-    {
-#pragma unroll
-        for (int k = 0; k < WB; ++k)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) t[k][b] = gt[(k * 4 + b) * 32 + lane];
-    }
-    __device__ __forceinline__ float get(const int k, const int b) const { return t[k][b]; }
-};
-template <int WB> struct Tab<WB, true> {
+// Register-resident log-odds table of one PWM of one lane: pairs P(k,b) = {T[k][b] (forward), Trc[k][b] (reverse
+// complement)}.  With the RC table padded at its HEAD (rows k < WB-W are zero) Trc[k][b] = T[WB-1-k][3-b] holds for
+// every k, hence P(WB-1-k, 3-b) is P(k,b) with its halves swapped -- and FADD2 takes a half-swapped operand for free
+// (SASS operand modifier .F32x2.LO_HI).  Only half of the pairs are kept: 4*WB registers instead of 8*WB, which is
+// what buys the extra resident warps.
+template <int WB> struct Tab {
     static constexpr int H = WB / 2;
     float2 h[H][4];
     float2 hm[2];  // middle row (odd WB): bases A, C; G and T are their swapped partners
@@ -96,28 +70,19 @@ template <int WB> struct Tab<WB, true> {
     }
 };
 
-constexpr int kQCap = 16;        // per-lane candidate queue slots (a block of kU steps adds at most 2*kU)
+constexpr int kQCap = 16;        // per-lane candidate queue slots
 constexpr int kStageCap = 128;   // per-warp staged hits
-constexpr int kStageFlush = 64;  // flush when more than this many are staged (one event adds <= 32)
-#ifndef SMG_KU
-#define SMG_KU 4
-#endif
-constexpr int kU = SMG_KU;       // steps between threshold checks on the ACGT fast path (divides 16)
+constexpr int kStageFlush = 64;  // flush when more than this many are staged (one pass adds <= 32)
+constexpr int kU = 4;            // steps between threshold checks on the ACGT fast path (divides 16)
 
-// one shift-register step for base B (compile-time); O receives the completed window score
-#define SMG_STEP(B, O)                                                                        \
-    {                                                                                         \
-        O = vadd(r[WB - 2], t.get(WB - 1, B));                                                \
-        _Pragma("unroll") for (int k = WB - 2; k >= 1; --k) r[k] = vadd(r[k - 1], t.get(k, B)); \
-        r[0] = t.get(0, B);                                                                   \
-    }
-
-#define SMG_SWITCH_STEP(b, O)      \
-    switch (b) {                   \
-    case 0: SMG_STEP(0, O); break; \
-    case 1: SMG_STEP(1, O); break; \
-    case 2: SMG_STEP(2, O); break; \
-    default: SMG_STEP(3, O); break; \
+// one shift-register step for base B (compile-time) of all NM PWMs of the lane; o[m][U] receives the completed scores
+#define SMG_STEP(B, U)                                                                                     \
+    {                                                                                                      \
+        _Pragma("unroll") for (int m_ = 0; m_ < NM; ++m_) {                                                \
+            o[m_][U] = vadd(r[m_][WB - 2], t[m_].get(WB - 1, B));                                          \
+            _Pragma("unroll") for (int k = WB - 2; k >= 1; --k) r[m_][k] = vadd(r[m_][k - 1], t[m_].get(k, B)); \
+            r[m_][0] = t[m_].get(0, B);                                                                    \
+        }                                                                                                  \
     }
 
 // Threaded dispatch: the body of step u first evaluates the two bit tests of step u+1's base straight off the packed
@@ -134,18 +99,19 @@ constexpr int kU = SMG_KU;       // steps between threshold checks on the ACGT f
 // default heuristic and lose occupancy; measured).  Registers are partitioned per SM sub-partition (16K each), so
 // the occupancy steps are 64/72/80/96/128/168 registers = 8/7/6/5/4/3 one-warp CTAs per sub-partition; the caps
 // below are the measured best step for each width (tools/bench_widths.py).
-template <int WB, bool DUAL> struct MaxRegs {
 #ifndef SMG_REGCAPS
 #define SMG_REGCAPS(WB) ((WB) <= 6 ? 72 : (WB) <= 8 ? 80 : (WB) <= 10 ? 96 : (WB) <= 12 ? 104 : (WB) <= 16 ? 128 : (WB) <= 24 ? 168 : 240)
 #endif
-    static constexpr int v = DUAL ? SMG_REGCAPS(WB) : (WB <= 19 ? 144 : WB <= 26 ? 168 : 240);
-};
+#ifndef SMG_REGCAPS2
+#define SMG_REGCAPS2(WB) ((WB) <= 8 ? 128 : 168)
+#endif
+template <int WB, int NM> struct MaxRegs { static constexpr int v = NM == 1 ? SMG_REGCAPS(WB) : SMG_REGCAPS2(WB); };
 
-template <int WB, bool DUAL>
-__global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, DUAL>::v)) scan_regtab_kernel(const ScanParams p)
+template <int WB, int NM>
+__global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, NM>::v)) scan_regtab_kernel(const ScanParams p)
 {
-    static_assert(WB >= 2 && WB <= SMG_MAX_REGTAB_WIDTH, "unsupported padded width");
-    using V = typename VecOf<DUAL>::T;
+    static_assert(WB >= 2 && WB <= SMG_MAX_REGTAB_WIDTH && NM >= 1 && NM <= SMG_MAX_PWMS_PER_LANE, "unsupported shape");
+    using V = float2;
     __shared__ unsigned long long s_keys[kStageCap];
     __shared__ float s_scores[kStageCap];
     __shared__ uint2 s_q[kQCap][32];  // per-lane candidate queues, [slot][lane] (bank-conflict free)
@@ -155,19 +121,21 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, DUAL>::v)) scan_r
     const int group = p.first_group + blockIdx.y;
     const smg_chunk_t ch = p.chunks[blockIdx.x];
     const smg_row_t row = p.rows[ch.row];
+    const float pinf = __int_as_float(0x7f800000);
 
-    // ---- per-lane PWM: table into registers, thresholds, trim bound
-    Tab<WB, DUAL> t;
-    t.load(p.group_tab + p.group_tab_off[group], lane);
-    const int motif = p.lane_motif[group * 32 + lane];
-    const int my_strand = DUAL ? 0 : p.lane_strand[group * 32 + lane];
-    const bool active = motif >= 0 && (DUAL || ((p.strands >> my_strand) & 1));
-    const int wm = motif >= 0 ? p.motif_width[motif] : 0;
-    const int rc_shift = DUAL ? (WB - (motif >= 0 ? wm : WB)) : 0;  // RC table is head-padded: its window starts later
-    const float thr_lo = active ? p.thr_lo[motif] : __int_as_float(0x7f800000);
-    const float thr_hi = active ? p.thr_hi[motif] : __int_as_float(0x7f800000);
-    const long long smax64 = row.g_len - row.g_off - (long long)wm;  // largest window start that fits (row-local)
-    const int smax = smax64 > 0x7fffffffLL ? 0x7fffffff : (smax64 < -1 ? -1 : (int)smax64);
+    // ---- per-lane PWMs: tables into registers, thresholds, trim bounds
+    Tab<WB> t[NM];
+    int motif[NM], wm[NM];
+    float thr_lo[NM], thr_hi[NM];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+        t[m].load(p.group_tab + p.group_tab_off[group] + (size_t)m * (WB * 4 * 32 * 2), lane);
+        motif[m] = p.lane_motif[(group * SMG_MAX_PWMS_PER_LANE + m) * 32 + lane];
+        wm[m] = motif[m] >= 0 ? p.motif_width[motif[m]] : WB;
+        thr_lo[m] = motif[m] >= 0 ? p.thr_lo[motif[m]] : pinf;
+        thr_hi[m] = motif[m] >= 0 ? p.thr_hi[motif[m]] : pinf;
+    }
+    const long long avail64 = row.g_len - row.g_off;  // smax (largest window start that fits) = avail64 - W
     const bool want_hits = p.hit_keys != nullptr;
     const int key_shift = p.pos_bits + p.motif_bits;
     const unsigned long long rowkey0 = (unsigned long long)(unsigned)p.out_rows[ch.row * 2 + 0] << key_shift;
@@ -181,11 +149,15 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, DUAL>::v)) scan_r
     const uint16_t* __restrict__ ap = p.amask + row.word_off + (c0 >> 4);
     const uint8_t* __restrict__ cp = p.codes ? p.codes + row.word_off * 16 : nullptr;
 
-    V r[WB - 1];
+    V r[NM][WB - 1];
 #pragma unroll
-    for (int k = 0; k < WB - 1; ++k) r[k] = V{};
-    int cnt0 = 0, cnt1 = 0;  // definite hits of this lane on strand 0 / 1
-    int nst = 0;             // staged hits (warp-uniform)
+    for (int m = 0; m < NM; ++m)
+#pragma unroll
+        for (int k = 0; k < WB - 1; ++k) r[m][k] = make_float2(0.f, 0.f);
+    int cnt[NM][2];  // definite hits of this lane per PWM and strand
+#pragma unroll
+    for (int m = 0; m < NM; ++m) cnt[m][0] = cnt[m][1] = 0;
+    int nst = 0;  // staged hits (warp-uniform)
 
     auto flush = [&]() {
         unsigned long long base = 0;
@@ -202,15 +174,15 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, DUAL>::v)) scan_r
     };
 
     // Candidate handling.  Two levels keep the per-block cost low:
-    //  (1) push(): a lane whose completed window score exceeds thr_lo appends (step, strand, score) to ITS OWN
-    //      queue in shared memory -- predicated store + pointer bump, no ballot / shuffle / loop in the scan loop;
-    //  (2) drain(): when any queue is half full (and at the end of the chunk) the warp walks the queues together:
+    //  (1) push(): a lane whose completed window score exceeds thr_lo appends (step, PWM slot, strand, score) to ITS
+    //      OWN queue in shared memory -- predicated store + pointer bump, no ballot / shuffle / loop in the scan loop;
+    //  (2) drain(): when any queue may overflow (and at the end of the chunk) the warp walks the queues together:
     //      range / trim checks, definite-vs-near split, per-lane counters, ballot + prefix-popcount compaction into
     //      the warp stage, which is appended to the global hit list with one atomic per flush.
     const int s_origin = c0 - (WB - 1);  // window start completed by the first step of the chunk
     int qn = 0;
-    auto push = [&](const float v, const int step_rel, const int st) {
-        s_q[qn][lane] = make_uint2(((unsigned)step_rel << 1) | (unsigned)st, __float_as_uint(v));
+    auto push = [&](const float v, const int step_rel, const int m, const int st) {
+        s_q[qn][lane] = make_uint2(((unsigned)step_rel << 2) | ((unsigned)m << 1) | (unsigned)st, __float_as_uint(v));
         ++qn;
     };
     auto drain = [&]() {
@@ -219,18 +191,29 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, DUAL>::v)) scan_r
             const bool have = j < qn;
             const uint2 e = have ? s_q[j][lane] : make_uint2(0u, 0u);
             const float v = __uint_as_float(e.y);
-            const int st = DUAL ? (int)(e.x & 1u) : my_strand;
-            const int s = s_origin + (int)(e.x >> 1) + (st ? rc_shift : 0);
-            const bool cand = have && (s >= c0) && (s < c1) && (s <= smax) && (DUAL ? ((p.strands >> st) & 1) : true);
-            const bool hit = cand && (v > thr_hi);
+            const int st = (int)(e.x & 1u);
+            const int sub = NM > 1 ? (int)((e.x >> 1) & 1u) : 0;
+            const int my_motif = (NM > 1 && sub) ? motif[NM - 1] : motif[0];
+            const int my_w = (NM > 1 && sub) ? wm[NM - 1] : wm[0];
+            const float my_hi = (NM > 1 && sub) ? thr_hi[NM - 1] : thr_hi[0];
+            // the RC table is head-padded: its completed window starts WB - W bases later
+            const int s = s_origin + (int)(e.x >> 2) + (st ? (WB - my_w) : 0);
+            const long long smax64 = avail64 - (long long)my_w;
+            const bool cand = have && (s >= c0) && (s < c1) && ((long long)s <= smax64) && ((p.strands >> st) & 1);
+            const bool hit = cand && (v > my_hi);
             if (hit) {
-                if (st) ++cnt1; else ++cnt0;
+#pragma unroll
+                for (int m = 0; m < NM; ++m) {
+                    if (sub == m) {
+                        if (st) ++cnt[m][1]; else ++cnt[m][0];
+                    }
+                }
             }
             if (cand && !hit) {  // near-threshold band: defer to the fp64 adjudicator
                 const unsigned long long i = atomicAdd(&p.counters[SMG_CTR_NEAR], 1ull);
                 if (i < p.near_cap) {
                     smg_near_t n;
-                    n.row = ch.row; n.motif = motif; n.strand = st; n.start = s; n.score = v; n.reserved = 0;
+                    n.row = ch.row; n.motif = my_motif; n.strand = st; n.start = s; n.score = v; n.reserved = 0;
                     p.near[i] = n;
                 }
             }
@@ -241,7 +224,7 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, DUAL>::v)) scan_r
                         const long long pos = st ? (smax64 - (long long)s) : (row.g_off + (long long)s);
                         const int slot = nst + __popc(hm & lt_mask);
                         s_keys[slot] = (st ? rowkey1 : rowkey0) | ((unsigned long long)pos << p.motif_bits) |
-                                       (unsigned long long)(unsigned)motif;
+                                       (unsigned long long)(unsigned)my_motif;
                         s_scores[slot] = v;
                     }
                     nst += __popc(hm);
@@ -264,64 +247,84 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, DUAL>::v)) scan_r
             // ---- ACGT fast path: 16 bases, threshold check every kU steps
 #pragma unroll 1
             for (int blk = 0; blk < 16 / kU; ++blk) {
-                V o[kU];
+                V o[NM][kU];
                 static_assert(kU == 4, "the threaded dispatch below is written for groups of 4 steps");
                 if (w & 2u) { if (w & 1u) goto sA3; else goto sA2; } else { if (w & 1u) goto sA1; else goto sA0; }
-                sA0: SMG_STEP(0, o[0]); SMG_GOTO_NEXT(0, w, sB)
-                sA1: SMG_STEP(1, o[0]); SMG_GOTO_NEXT(0, w, sB)
-                sA2: SMG_STEP(2, o[0]); SMG_GOTO_NEXT(0, w, sB)
-                sA3: SMG_STEP(3, o[0]); SMG_GOTO_NEXT(0, w, sB)
-                sB0: SMG_STEP(0, o[1]); SMG_GOTO_NEXT(1, w, sC)
-                sB1: SMG_STEP(1, o[1]); SMG_GOTO_NEXT(1, w, sC)
-                sB2: SMG_STEP(2, o[1]); SMG_GOTO_NEXT(1, w, sC)
-                sB3: SMG_STEP(3, o[1]); SMG_GOTO_NEXT(1, w, sC)
-                sC0: SMG_STEP(0, o[2]); SMG_GOTO_NEXT(2, w, sD)
-                sC1: SMG_STEP(1, o[2]); SMG_GOTO_NEXT(2, w, sD)
-                sC2: SMG_STEP(2, o[2]); SMG_GOTO_NEXT(2, w, sD)
-                sC3: SMG_STEP(3, o[2]); SMG_GOTO_NEXT(2, w, sD)
-                sD0: SMG_STEP(0, o[3]); goto sEnd;
-                sD1: SMG_STEP(1, o[3]); goto sEnd;
-                sD2: SMG_STEP(2, o[3]); goto sEnd;
-                sD3: SMG_STEP(3, o[3]);
+                sA0: SMG_STEP(0, 0); SMG_GOTO_NEXT(0, w, sB)
+                sA1: SMG_STEP(1, 0); SMG_GOTO_NEXT(0, w, sB)
+                sA2: SMG_STEP(2, 0); SMG_GOTO_NEXT(0, w, sB)
+                sA3: SMG_STEP(3, 0); SMG_GOTO_NEXT(0, w, sB)
+                sB0: SMG_STEP(0, 1); SMG_GOTO_NEXT(1, w, sC)
+                sB1: SMG_STEP(1, 1); SMG_GOTO_NEXT(1, w, sC)
+                sB2: SMG_STEP(2, 1); SMG_GOTO_NEXT(1, w, sC)
+                sB3: SMG_STEP(3, 1); SMG_GOTO_NEXT(1, w, sC)
+                sC0: SMG_STEP(0, 2); SMG_GOTO_NEXT(2, w, sD)
+                sC1: SMG_STEP(1, 2); SMG_GOTO_NEXT(2, w, sD)
+                sC2: SMG_STEP(2, 2); SMG_GOTO_NEXT(2, w, sD)
+                sC3: SMG_STEP(3, 2); SMG_GOTO_NEXT(2, w, sD)
+                sD0: SMG_STEP(0, 3); goto sEnd;
+                sD1: SMG_STEP(1, 3); goto sEnd;
+                sD2: SMG_STEP(2, 3); goto sEnd;
+                sD3: SMG_STEP(3, 3);
                 sEnd:
                 w >>= 2 * kU;
-                float m = vmax(o[0]);
+                bool any_c = false;
 #pragma unroll
-                for (int u = 1; u < kU; ++u) m = vmax3(m, o[u]);
-                if (__any_sync(SMG_FULL_MASK, m > thr_lo)) {
+                for (int m = 0; m < NM; ++m) {
+                    float mx = fmaxf(o[m][0].x, o[m][0].y);
+#pragma unroll
+                    for (int u = 1; u < kU; ++u) mx = vmax3(mx, o[m][u]);
+                    any_c = any_c || (mx > thr_lo[m]);
+                }
+                if (__any_sync(SMG_FULL_MASK, any_c)) {
                     const int rel = wi * 16 + blk * kU;
 #pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-                        if (vget(o[u], 0) > thr_lo) push(vget(o[u], 0), rel + u, 0);
-                        if (DUAL) {
-                            if (vget(o[u], 1) > thr_lo) push(vget(o[u], 1), rel + u, 1);
+                    for (int m = 0; m < NM; ++m) {
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) {
+                            if (o[m][u].x > thr_lo[m]) push(o[m][u].x, rel + u, m, 0);
+                            if (o[m][u].y > thr_lo[m]) push(o[m][u].y, rel + u, m, 1);
                         }
+                        // a block adds at most 2*kU entries per PWM slot: drain before the next slot could overflow
+                        if (__any_sync(SMG_FULL_MASK, qn > kQCap - 2 * kU)) drain();
                     }
-                    if (__any_sync(SMG_FULL_MASK, qn > kQCap - 2 * kU)) drain();
                 }
             }
         } else {
             // ---- generic path: IUPAC ambiguity codes, 'Z', and the padding past the end of the row
 #pragma unroll 1
             for (int j = 0; j < 16; ++j) {
-                V o;
+                V o[NM][1];
                 if (((am >> j) & 1u) == 0) {
-                    const uint32_t b = (w >> (2 * j)) & 3u;
-                    SMG_SWITCH_STEP(b, o);
+                    switch ((w >> (2 * j)) & 3u) {
+                    case 0: SMG_STEP(0, 0); break;
+                    case 1: SMG_STEP(1, 0); break;
+                    case 2: SMG_STEP(2, 0); break;
+                    default: SMG_STEP(3, 0); break;
+                    }
                 } else {
                     const int q = s_base + (WB - 1) + j;  // row-local position of this base
                     const int code = (cp != nullptr && q < row.n_avail) ? (int)cp[q] : 0;
                     const float e0 = c_emb[code][0], e1 = c_emb[code][1], e2 = c_emb[code][2], e3 = c_emb[code][3];
-                    o = vadd(r[WB - 2], vmix(e0, e1, e2, e3, t.get(WB - 1, 0), t.get(WB - 1, 1), t.get(WB - 1, 2), t.get(WB - 1, 3)));
 #pragma unroll
-                    for (int k = WB - 2; k >= 1; --k)
-                        r[k] = vadd(r[k - 1], vmix(e0, e1, e2, e3, t.get(k, 0), t.get(k, 1), t.get(k, 2), t.get(k, 3)));
-                    r[0] = vmix(e0, e1, e2, e3, t.get(0, 0), t.get(0, 1), t.get(0, 2), t.get(0, 3));
+                    for (int m = 0; m < NM; ++m) {
+                        o[m][0] = vadd(r[m][WB - 2], vmix(e0, e1, e2, e3, t[m].get(WB - 1, 0), t[m].get(WB - 1, 1),
+                                                          t[m].get(WB - 1, 2), t[m].get(WB - 1, 3)));
+#pragma unroll
+                        for (int k = WB - 2; k >= 1; --k)
+                            r[m][k] = vadd(r[m][k - 1], vmix(e0, e1, e2, e3, t[m].get(k, 0), t[m].get(k, 1), t[m].get(k, 2),
+                                                             t[m].get(k, 3)));
+                        r[m][0] = vmix(e0, e1, e2, e3, t[m].get(0, 0), t[m].get(0, 1), t[m].get(0, 2), t[m].get(0, 3));
+                    }
                 }
-                if (__any_sync(SMG_FULL_MASK, vmax(o) > thr_lo)) {
-                    if (vget(o, 0) > thr_lo) push(vget(o, 0), wi * 16 + j, 0);
-                    if (DUAL) {
-                        if (vget(o, 1) > thr_lo) push(vget(o, 1), wi * 16 + j, 1);
+                bool any_c = false;
+#pragma unroll
+                for (int m = 0; m < NM; ++m) any_c = any_c || (fmaxf(o[m][0].x, o[m][0].y) > thr_lo[m]);
+                if (__any_sync(SMG_FULL_MASK, any_c)) {
+#pragma unroll
+                    for (int m = 0; m < NM; ++m) {
+                        if (o[m][0].x > thr_lo[m]) push(o[m][0].x, wi * 16 + j, m, 0);
+                        if (o[m][0].y > thr_lo[m]) push(o[m][0].y, wi * 16 + j, m, 1);
                     }
                     if (__any_sync(SMG_FULL_MASK, qn > kQCap - 2 * kU)) drain();
                 }
@@ -334,22 +337,26 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, DUAL>::v)) scan_r
 
     drain();
     if (want_hits && nst > 0) flush();
-    if (p.counts != nullptr && motif >= 0) {
-        int32_t* c = p.counts + ((size_t)ch.row * p.n_motifs + motif) * 2;
-        if (cnt0) atomicAdd(c + 0, cnt0);
-        if (cnt1) atomicAdd(c + 1, cnt1);
+    int tot = 0;
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+        if (p.counts != nullptr && motif[m] >= 0) {
+            int32_t* c = p.counts + ((size_t)ch.row * p.n_motifs + motif[m]) * 2;
+            if (cnt[m][0]) atomicAdd(c + 0, cnt[m][0]);
+            if (cnt[m][1]) atomicAdd(c + 1, cnt[m][1]);
+        }
+        tot += cnt[m][0] + cnt[m][1];
     }
-    int tot = cnt0 + cnt1;
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) tot += __shfl_xor_sync(SMG_FULL_MASK, tot, d);
     if (lane == 0 && tot) atomicAdd(&p.counters[SMG_CTR_DEFINITE], (unsigned long long)tot);
 }
 
-template <int WB, bool DUAL>
+template <int WB, int NM>
 void launch_scan_regtab(const ScanParams& p, int n_chunks, int n_groups, cudaStream_t stream)
 {
     dim3 grid((unsigned)n_chunks, (unsigned)n_groups, 1);
-    scan_regtab_kernel<WB, DUAL><<<grid, 32, 0, stream>>>(p);
+    scan_regtab_kernel<WB, NM><<<grid, 32, 0, stream>>>(p);
 }
 
 }  // namespace smg

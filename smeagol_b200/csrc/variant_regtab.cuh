@@ -21,6 +21,13 @@ struct VariantParams {
     unsigned int* slow_flags;  // [n_snv] set when the SNV needs the generic path (ambiguity codes in the region)
 };
 
+#define SMG_VSTEP(B, O)                                                                       \
+    {                                                                                         \
+        O = vadd(r[WB - 2], t.get(WB - 1, B));                                                \
+        _Pragma("unroll") for (int k = WB - 2; k >= 1; --k) r[k] = vadd(r[k - 1], t.get(k, B)); \
+        r[0] = t.get(0, B);                                                                   \
+    }
+
 template <int WB>
 __global__ void __launch_bounds__(32) variant_regtab_kernel(const VariantParams vp)
 {
@@ -28,9 +35,10 @@ __global__ void __launch_bounds__(32) variant_regtab_kernel(const VariantParams 
     const ScanParams& p = vp.sp;
     const int lane = threadIdx.x;
     const int group = p.first_group + blockIdx.y;
-    Tab<WB, true> t;
-    t.load(p.group_tab + p.group_tab_off[group], lane);
-    const int motif = p.lane_motif[group * 32 + lane];
+    const int sub = blockIdx.z;  // PWM slot of the lane group handled by this CTA
+    Tab<WB> t;
+    t.load(p.group_tab + p.group_tab_off[group] + (size_t)sub * (WB * 4 * 32 * 2), lane);
+    const int motif = p.lane_motif[(group * SMG_MAX_PWMS_PER_LANE + sub) * 32 + lane];
     const int wm = motif >= 0 ? p.motif_width[motif] : 1;
     const int rc_shift = WB - (motif >= 0 ? wm : WB);  // head-padded RC table: its window completes rc_shift steps earlier
     const float ninf = __int_as_float(0xff800000);
@@ -45,7 +53,7 @@ __global__ void __launch_bounds__(32) variant_regtab_kernel(const VariantParams 
         unsigned long long lo = 0, hi = 0;
         bool slow = (alt < 1 || alt > 5);
         if (pos < 0 || pos >= row.n_avail) {  // out of range: the generic kernel reports -inf
-            if (lane == 0 && blockIdx.y == 0) vp.slow_flags[v] = 1u;
+            if (lane == 0 && blockIdx.y == 0 && blockIdx.z == 0) vp.slow_flags[v] = 1u;
             continue;
         }
         {
@@ -79,7 +87,7 @@ __global__ void __launch_bounds__(32) variant_regtab_kernel(const VariantParams 
             }
         }
         if (slow) {  // warp-uniform: leave this SNV to the generic kernel
-            if (lane == 0 && blockIdx.y == 0) vp.slow_flags[v] = 1u;
+            if (lane == 0 && blockIdx.y == 0 && blockIdx.z == 0) vp.slow_flags[v] = 1u;
             continue;
         }
         // per-lane range of steps whose completed window is valid: covers pos, starts >= 0, ends inside the sequence
@@ -107,9 +115,9 @@ __global__ void __launch_bounds__(32) variant_regtab_kernel(const VariantParams 
             for (int i = 0; i < NSTEP; ++i) {
                 V o;
                 if (L0 & 2ull) {
-                    if (L0 & 1ull) SMG_STEP(3, o) else SMG_STEP(2, o)
+                    if (L0 & 1ull) SMG_VSTEP(3, o) else SMG_VSTEP(2, o)
                 } else {
-                    if (L0 & 1ull) SMG_STEP(1, o) else SMG_STEP(0, o)
+                    if (L0 & 1ull) SMG_VSTEP(1, o) else SMG_VSTEP(0, o)
                 }
                 L0 = (L0 >> 2) | (H0 << 62);
                 H0 >>= 2;
@@ -126,9 +134,9 @@ __global__ void __launch_bounds__(32) variant_regtab_kernel(const VariantParams 
 }
 
 template <int WB>
-void launch_variant_regtab(const VariantParams& vp, int n_blocks, int n_groups, cudaStream_t stream)
+void launch_variant_regtab(const VariantParams& vp, int n_blocks, int n_groups, int nm, cudaStream_t stream)
 {
-    dim3 grid((unsigned)n_blocks, (unsigned)n_groups, 1);
+    dim3 grid((unsigned)n_blocks, (unsigned)n_groups, (unsigned)nm);
     variant_regtab_kernel<WB><<<grid, 32, 0, stream>>>(vp);
 }
 
