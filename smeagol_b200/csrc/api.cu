@@ -114,6 +114,10 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ s
                                                    uint16_t* __restrict__ amask, uint8_t* __restrict__ codes,
                                                    unsigned long long* __restrict__ status)
 {
+    // the 256-entry LUT is read with per-lane (divergent) indices: shared memory, not the constant cache
+    __shared__ uint8_t s_lut[256];
+    s_lut[threadIdx.x] = c_lut[threadIdx.x];
+    __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < total_words; wi += stride) {
         int lo = 0, hi = n_rows - 1;  // largest r with rows[r].word_off <= wi
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ s
         for (int j = 0; j < 16; ++j) {
             int code = 0;
             if (j < rem) {
-                code = kind ? (int)raw[j] : (int)c_lut[raw[j]];
+                code = kind ? (int)raw[j] : (int)s_lut[raw[j]];
                 if (code > 16) {  // KeyError in the reference (encode.py:66)
                     atomicMin(&status[0], (unsigned long long)(so + q0 + j));
                     code = 0;
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ s
         }
         packed[wi] = pw;
         amask[wi] = (uint16_t)aw;
-        if (codes) {
+        if (codes && aw) {  // codes are only ever read where the mask is set: skip the 1 B/base write for plain words
             uint4 v;
             memcpy(&v, cd, 16);
             *reinterpret_cast<uint4*>(codes + wi * 16) = v;
@@ -508,7 +512,7 @@ int smg_pack(const uint8_t* d_src, int input_kind, const smg_row_t* d_rows, cons
         return fail(SMG_ERR_INVALID, "smg_pack: bad argument");
     int rc = init_lut();
     if (rc != SMG_OK) return rc;
-    const int64_t blocks = std::min<int64_t>((total_words + 255) / 256, 148 * 32);
+    const int64_t blocks = std::min<int64_t>((total_words + 255) / 256, 148 * 64);
     pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_src, input_kind, d_rows, d_src_off, n_rows, total_words,
                                                                     d_packed, d_amask, d_codes,
                                                                     reinterpret_cast<unsigned long long*>(d_status));

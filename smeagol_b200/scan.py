@@ -27,9 +27,22 @@ def _score_base(pwm, base, pos):
     return np.sum(np.multiply(pwm[pos, :], one_hot_dict[base]))
 
 
-def _sites_frame(ids, names, senses, pos_idx, pwm_idx, model, scores=None):
-    sites = pd.DataFrame({"id": ids, "name": names, "sense": senses, "start": pos_idx,
-                          "Matrix_id": model.Matrix_ids[pwm_idx]})
+def _take(labels, idx):
+    """labels[idx] as a DataFrame column.  pandas >= 3 converts object arrays of str element by element; converting the
+    (short) label array once and gathering with take() keeps large site lists cheap."""
+    labels = np.asarray(labels)
+    idx = np.asarray(idx, dtype=np.int64)
+    if labels.dtype.kind not in "OUS":
+        return labels[idx]
+    try:
+        return pd.array(labels).take(idx)
+    except Exception:
+        return labels.astype(object)[idx]
+
+
+def _sites_frame(ids, names, senses, row_idx, pos_idx, pwm_idx, model, scores=None):
+    sites = pd.DataFrame({"id": _take(ids, row_idx), "name": _take(names, row_idx), "sense": _take(senses, row_idx),
+                          "start": pos_idx, "Matrix_id": _take(model.Matrix_ids, pwm_idx)})
     sites["width"] = model.widths[pwm_idx]
     sites["end"] = sites["start"] + sites["width"]
     if scores is not None:
@@ -42,8 +55,7 @@ def _sites_frame(ids, names, senses, pos_idx, pwm_idx, model, scores=None):
 def _locate_sites(encoding, model, thresholded, scores=None):
     """DataFrame of binding sites from a thresholded triple (scan.py:40-74); same columns and order."""
     seq_idx, pos_idx, pwm_idx = (np.asarray(t) for t in thresholded)
-    return _sites_frame(encoding.ids[seq_idx], encoding.names[seq_idx], encoding.senses[seq_idx], pos_idx, pwm_idx,
-                        model, scores)
+    return _sites_frame(encoding.ids, encoding.names, encoding.senses, seq_idx, pos_idx, pwm_idx, model, scores)
 
 
 _EMPTY_COUNTS = ["Matrix_id", "width", "id", "name", "sense", "num"]
@@ -54,29 +66,45 @@ def _melt_counts(table, row_labels, model, extra=None):
     one group; rows kept = PWMs with >=1 hit, columns kept = (id, name, sense) labels with >=1 hit; output iterates
     sorted columns (outer) x sorted (Matrix_id, width) (inner)."""
     ids, names, senses = row_labels
-    col_keys = pd.MultiIndex.from_arrays([ids, names, senses])
-    # rows of the encoding sharing (id, name, sense) collapse into one crosstab column
-    col_codes, col_uniques = pd.factorize(col_keys, sort=True)
+    # rows of the encoding sharing (id, name, sense) collapse into one crosstab column; columns are sorted tuples
+    keys = list(zip(ids, names, senses))
+    col_uniques = sorted(set(keys))
+    pos_of = {k: i for i, k in enumerate(col_uniques)}
+    col_codes = np.fromiter((pos_of[k] for k in keys), dtype=np.int64, count=len(keys))
     n_cols = len(col_uniques)
-    agg = np.zeros((n_cols, table.shape[1]), dtype=np.int64)
-    np.add.at(agg, col_codes, table)
+    if n_cols == len(keys):
+        agg = np.empty((n_cols, table.shape[1]), dtype=np.int64)
+        agg[col_codes] = table
+    else:
+        agg = np.zeros((n_cols, table.shape[1]), dtype=np.int64)
+        np.add.at(agg, col_codes, table)
     keep_cols = np.flatnonzero(agg.sum(axis=1) > 0)
     keep_m = np.flatnonzero(agg.sum(axis=0) > 0)
     if keep_cols.size == 0:
         return pd.DataFrame({k: [] for k in _EMPTY_COUNTS})
-    m_order = keep_m[pd.DataFrame({"a": model.Matrix_ids[keep_m], "b": model.widths[keep_m]})
-                     .sort_values(["a", "b"], kind="stable").index.to_numpy()]
+    m_order = keep_m[np.argsort(_motif_rank(model)[keep_m], kind="stable")]
     sub = agg[np.ix_(keep_cols, m_order)]
-    cu = col_uniques[keep_cols]
     nm = len(m_order)
+    rep = np.repeat(keep_cols, nm)
     return pd.DataFrame({
-        "Matrix_id": np.tile(model.Matrix_ids[m_order], len(keep_cols)),
+        "Matrix_id": _take(model.Matrix_ids, np.tile(m_order, len(keep_cols))),
         "width": np.tile(model.widths[m_order], len(keep_cols)),
-        "id": np.repeat(np.array([c[0] for c in cu], dtype=object), nm),
-        "name": np.repeat(np.array([c[1] for c in cu], dtype=object), nm),
-        "sense": np.repeat(np.array([c[2] for c in cu], dtype=object), nm),
+        "id": _take([c[0] for c in col_uniques], rep),
+        "name": _take([c[1] for c in col_uniques], rep),
+        "sense": _take([c[2] for c in col_uniques], rep),
         "num": sub.reshape(-1),
     })
+
+
+def _motif_rank(model):
+    """Rank of every PWM in the crosstab's row order: sorted by (Matrix_id, width) (scan.py:137-140)."""
+    rank = getattr(model, "_crosstab_rank", None)
+    if rank is None:
+        order = sorted(range(model.channels), key=lambda i: (model.Matrix_ids[i], model.widths[i]))
+        rank = np.empty(model.channels, dtype=np.int64)
+        rank[order] = np.arange(model.channels)
+        model._crosstab_rank = rank
+    return rank
 
 
 def _count_sites(encoding, model, thresholded):
@@ -165,8 +193,7 @@ def _find_sites_in_groups(encoding, model, threshold, outputs=["sites"], score=F
                 frames.append(_bin_sites_by_score(g, model, (row[sel] - gfo[gi], pos[sel], motif[sel]), sc[sel], threshold))
             output["binned_counts"] = pd.concat(frames).reset_index(drop=True)
         if "sites" in outputs:
-            output["sites"] = _sites_frame(ids_all[row], names_all[row], senses_all[row], pos, motif, model,
-                                           sc if score else None)
+            output["sites"] = _sites_frame(ids_all, names_all, senses_all, row, pos, motif, model, sc if score else None)
     if want_counts:
         counts_dev = res.counts.cpu().numpy().astype(np.int64)  # (n_device_rows, M, 2)
         table = np.zeros((layout["n_out"], model.channels), dtype=np.int64)
