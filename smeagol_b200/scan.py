@@ -41,15 +41,17 @@ def _take(labels, idx):
 
 
 def _sites_frame(ids, names, senses, row_idx, pos_idx, pwm_idx, model, scores=None):
-    sites = pd.DataFrame({"id": _take(ids, row_idx), "name": _take(names, row_idx), "sense": _take(senses, row_idx),
-                          "start": pos_idx, "Matrix_id": _take(model.Matrix_ids, pwm_idx)})
-    sites["width"] = model.widths[pwm_idx]
-    sites["end"] = sites["start"] + sites["width"]
+    """One DataFrame construction with the reference's column order (scan.py:59-73)."""
+    pos_idx = np.asarray(pos_idx)
+    width = model.widths[pwm_idx]
+    cols = {"id": _take(ids, row_idx), "name": _take(names, row_idx), "sense": _take(senses, row_idx), "start": pos_idx,
+            "Matrix_id": _take(model.Matrix_ids, pwm_idx), "width": width, "end": pos_idx + width}
     if scores is not None:
-        sites["score"] = scores
-        sites["max_score"] = model.max_scores[pwm_idx]
-        sites["frac_score"] = sites["score"] / sites["max_score"]
-    return sites
+        max_score = model.max_scores[pwm_idx]
+        cols["score"] = scores
+        cols["max_score"] = max_score
+        cols["frac_score"] = scores / max_score
+    return pd.DataFrame(cols, copy=False)
 
 
 def _locate_sites(encoding, model, thresholded, scores=None):
