@@ -180,12 +180,17 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, NM>::v)) scan_reg
     //      range / trim checks, definite-vs-near split, per-lane counters, ballot + prefix-popcount compaction into
     //      the warp stage, which is appended to the global hit list with one atomic per flush.
     const int s_origin = c0 - (WB - 1);  // window start completed by the first step of the chunk
-    int qn = 0;
-    auto push = [&](const float v, const int step_rel, const int m, const int st) {
-        s_q[qn][lane] = make_uint2(((unsigned)step_rel << 2) | ((unsigned)m << 1) | (unsigned)st, __float_as_uint(v));
-        ++qn;
+    // the queue is addressed through a running shared-memory byte address: one predicated 8-byte store + one
+    // predicated add per candidate (tag = step index within the chunk, PWM slot, strand)
+    const unsigned qbase = (unsigned)__cvta_generic_to_shared(&s_q[0][lane]);
+    unsigned qaddr = qbase;
+    constexpr unsigned kQStride = 32 * sizeof(uint2);
+    auto push = [&](const float v, const unsigned tag) {
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(qaddr), "r"(tag), "f"(v) : "memory");
+        qaddr += kQStride;
     };
     auto drain = [&]() {
+        const int qn = (int)((qaddr - qbase) / kQStride);
         const int maxn = __reduce_max_sync(SMG_FULL_MASK, qn);
         for (int j = 0; j < maxn; ++j) {
             const bool have = j < qn;
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, NM>::v)) scan_reg
                 }
             }
         }
-        qn = 0;
+        qaddr = qbase;
         __syncwarp();
     };
 
@@ -277,16 +282,16 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, NM>::v)) scan_reg
                     any_c = any_c || (mx > thr_lo[m]);
                 }
                 if (__any_sync(SMG_FULL_MASK, any_c)) {
-                    const int rel = wi * 16 + blk * kU;
+                    const unsigned tag0 = (unsigned)(wi * 16 + blk * kU) << 2;
 #pragma unroll
                     for (int m = 0; m < NM; ++m) {
 #pragma unroll
                         for (int u = 0; u < kU; ++u) {
-                            if (o[m][u].x > thr_lo[m]) push(o[m][u].x, rel + u, m, 0);
-                            if (o[m][u].y > thr_lo[m]) push(o[m][u].y, rel + u, m, 1);
+                            if (o[m][u].x > thr_lo[m]) push(o[m][u].x, tag0 + (unsigned)((u << 2) | (m << 1)));
+                            if (o[m][u].y > thr_lo[m]) push(o[m][u].y, tag0 + (unsigned)((u << 2) | (m << 1) | 1));
                         }
                         // a block adds at most 2*kU entries per PWM slot: drain before the next slot could overflow
-                        if (__any_sync(SMG_FULL_MASK, qn > kQCap - 2 * kU)) drain();
+                        if (__any_sync(SMG_FULL_MASK, qaddr > qbase + (kQCap - 2 * kU) * kQStride)) drain();
                     }
                 }
             }
@@ -322,11 +327,13 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, NM>::v)) scan_reg
                 for (int m = 0; m < NM; ++m) any_c = any_c || (fmaxf(o[m][0].x, o[m][0].y) > thr_lo[m]);
                 if (__any_sync(SMG_FULL_MASK, any_c)) {
 #pragma unroll
+                    const unsigned tag0 = (unsigned)(wi * 16 + j) << 2;
+#pragma unroll
                     for (int m = 0; m < NM; ++m) {
-                        if (o[m][0].x > thr_lo[m]) push(o[m][0].x, wi * 16 + j, m, 0);
-                        if (o[m][0].y > thr_lo[m]) push(o[m][0].y, wi * 16 + j, m, 1);
+                        if (o[m][0].x > thr_lo[m]) push(o[m][0].x, tag0 + (unsigned)(m << 1));
+                        if (o[m][0].y > thr_lo[m]) push(o[m][0].y, tag0 + (unsigned)((m << 1) | 1));
                     }
-                    if (__any_sync(SMG_FULL_MASK, qn > kQCap - 2 * kU)) drain();
+                    if (__any_sync(SMG_FULL_MASK, qaddr > qbase + (kQCap - 2 * kU) * kQStride)) drain();
                 }
             }
         }
