@@ -70,7 +70,7 @@ template <int WB> struct Tab {
     }
 };
 
-constexpr int kQCap = 16;        // per-lane candidate queue slots
+constexpr int kQCap = 16;        // per-lane candidate queue slots (32 with two PWMs per lane)
 constexpr int kStageCap = 128;   // per-warp staged hits
 constexpr int kStageFlush = 64;  // flush when more than this many are staged (one pass adds <= 32)
 constexpr int kU = 4;            // steps between threshold checks on the ACGT fast path (divides 16)
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, NM>::v)) scan_reg
     using V = float2;
     __shared__ unsigned long long s_keys[kStageCap];
     __shared__ float s_scores[kStageCap];
-    __shared__ uint2 s_q[kQCap][32];  // per-lane candidate queues, [slot][lane] (bank-conflict free)
+    __shared__ uint2 s_q[kQCap * NM][32];  // per-lane candidate queues, [slot][lane] (bank-conflict free)
 
     const int lane = threadIdx.x;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -273,26 +273,33 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, NM>::v)) scan_reg
                 sD3: SMG_STEP(3, 3);
                 sEnd:
                 w >>= 2 * kU;
-                bool any_c = false;
+                // two-level check: one vote for the whole group of 4 steps, then one per half, so that a group with a
+                // single candidate issues 4 predicated pushes instead of 8
+                bool any_lo = false, any_hi = false;
 #pragma unroll
                 for (int m = 0; m < NM; ++m) {
-                    float mx = fmaxf(o[m][0].x, o[m][0].y);
-#pragma unroll
-                    for (int u = 1; u < kU; ++u) mx = vmax3(mx, o[m][u]);
-                    any_c = any_c || (mx > thr_lo[m]);
+                    const float m01 = vmax3(fmaxf(o[m][0].x, o[m][0].y), o[m][1]);
+                    const float m23 = vmax3(fmaxf(o[m][2].x, o[m][2].y), o[m][3]);
+                    any_lo = any_lo || (m01 > thr_lo[m]);
+                    any_hi = any_hi || (m23 > thr_lo[m]);
                 }
-                if (__any_sync(SMG_FULL_MASK, any_c)) {
+                if (__any_sync(SMG_FULL_MASK, any_lo || any_hi)) {
                     const unsigned tag0 = (unsigned)(wi * 16 + blk * kU) << 2;
 #pragma unroll
-                    for (int m = 0; m < NM; ++m) {
+                    for (int half = 0; half < 2; ++half) {
+                        if (__any_sync(SMG_FULL_MASK, half ? any_hi : any_lo)) {
 #pragma unroll
-                        for (int u = 0; u < kU; ++u) {
-                            if (o[m][u].x > thr_lo[m]) push(o[m][u].x, tag0 + (unsigned)((u << 2) | (m << 1)));
-                            if (o[m][u].y > thr_lo[m]) push(o[m][u].y, tag0 + (unsigned)((u << 2) | (m << 1) | 1));
+                            for (int m = 0; m < NM; ++m) {
+#pragma unroll
+                                for (int u = 2 * half; u < 2 * half + 2; ++u) {
+                                    if (o[m][u].x > thr_lo[m]) push(o[m][u].x, tag0 + (unsigned)((u << 2) | (m << 1)));
+                                    if (o[m][u].y > thr_lo[m]) push(o[m][u].y, tag0 + (unsigned)((u << 2) | (m << 1) | 1));
+                                }
+                            }
                         }
-                        // a block adds at most 2*kU entries per PWM slot: drain before the next slot could overflow
-                        if (__any_sync(SMG_FULL_MASK, qaddr > qbase + (kQCap - 2 * kU) * kQStride)) drain();
                     }
+                    // a group adds at most 2*kU entries per PWM slot
+                    if (__any_sync(SMG_FULL_MASK, qaddr > qbase + (kQCap * NM - 2 * kU * NM) * kQStride)) drain();
                 }
             }
         } else {
@@ -333,7 +340,7 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, NM>::v)) scan_reg
                         if (o[m][0].x > thr_lo[m]) push(o[m][0].x, tag0 + (unsigned)(m << 1));
                         if (o[m][0].y > thr_lo[m]) push(o[m][0].y, tag0 + (unsigned)((m << 1) | 1));
                     }
-                    if (__any_sync(SMG_FULL_MASK, qaddr > qbase + (kQCap - 2 * kU) * kQStride)) drain();
+                    if (__any_sync(SMG_FULL_MASK, qaddr > qbase + (kQCap * NM - 2 * kU * NM) * kQStride)) drain();
                 }
             }
         }

@@ -382,3 +382,48 @@ def test_benchmark_slice_full_parity_vs_c_oracle():
     ksum, kxor = res.key_checksum()
     assert ksum % (1 << 64) == exp["key_sum"] and kxor % (1 << 64) == exp["key_xor"]
     assert res.stats["n_near"] >= exp["n_near"]  # the kernel's fp32 band is a superset of the oracle's fp64 band
+
+
+def test_buffer_overflow_is_detected_and_retried():
+    """Hit / near-threshold buffers that are too small are regrown and the scan repeated -- never truncated."""
+    sb = _sb()
+    from smeagol_b200 import device as dev
+
+    rng = np.random.default_rng(31)
+    model = sb.models.PWMModel(synth_pwms(rng, 30, 6, 10))
+    seqs = [rand_seq(rng, 3000)]
+    batch = dev.SeqBatch(seqs)
+    out_rows = np.array([[0, 1]], dtype=np.int32)
+    thr = model.thresholds(1.0)  # every window at the maximum score is near-threshold
+    full = dev.scan(model.device_set, batch, model.thresholds(0.4), 3, out_rows, 2)
+    tiny = dev.scan(model.device_set, batch, model.thresholds(0.4), 3, out_rows, 2, hit_cap=7, near_cap=1)
+    assert tiny.stats["hit_cap"] >= full.n_hits > 7
+    for a, b in zip(full.hits_host(), tiny.hits_host()):
+        np.testing.assert_array_equal(a, b)
+    near = dev.scan(model.device_set, batch, thr, 3, out_rows, 2, near_cap=1)
+    exp = so.scan_rows(seqs, model.weights, 1.0, rcomp="both", order="kernel")
+    np.testing.assert_array_equal(near.hits_host()[1], exp["pos"])
+
+
+def test_edge_inputs():
+    """Empty and tiny rows, a row made only of N, sequences shorter than every PWM, a single PWM."""
+    sb = _sb()
+    rng = np.random.default_rng(37)
+    model = sb.models.PWMModel(synth_pwms(rng, 5, 6, 9))
+    seqs = ["", "A", "ACGTA", "N" * 50, rand_seq(rng, 200)]
+    check_against_oracle(model, seqs, 0.5, "both")
+    one = sb.models.PWMModel(synth_pwms(rng, 1, 8, 8))
+    check_against_oracle(one, [rand_seq(rng, 500)], 0.5, "both")
+    recs = [sb.SeqRecord(sb.Seq("ACG"), id="s", name="s")]
+    out = sb.scan.scan_sequences(recs, model, 0.5, rcomp="both", outputs=["sites", "counts"], score=True)
+    assert len(out["sites"]) == 0 and len(out["counts"]) == 0
+    assert list(out["sites"].columns) == ["id", "name", "sense", "start", "Matrix_id", "width", "end", "score", "max_score",
+                                          "frac_score"]
+    assert list(out["counts"].columns) == ["Matrix_id", "width", "id", "name", "sense", "num"]
+    with pytest.raises(KeyError):
+        sb.scan.scan_sequences([sb.SeqRecord(sb.Seq("ACGTX"), id="s", name="s")], model, 0.5)
+    with pytest.raises(ValueError):
+        sb.scan.scan_sequences([sb.SeqRecord(sb.Seq("ACGT"), id="a", name="g"), sb.SeqRecord(sb.Seq("ACG"), id="b", name="g")],
+                               model, 0.5, group_by="name")
+    with pytest.raises(AssertionError):
+        sb.scan.scan_sequences(recs, model, 1.5)
