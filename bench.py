@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=120, help="genomes in the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", default=None, choices=["regtab", "hmma"], help="scan engine (default: the library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,7 +191,8 @@ def main():
     host_flat, src_off = dev.flatten_rows(genomes, pinned=True)
     lens = np.array([g.shape[0] for g in genomes], dtype=np.int64)
     batch = dev.SeqBatch(None, flat=(host_flat, src_off, lens))
-    plan = dev.ScanPlan(dset, batch, thr, 3, out_rows, 2 * n, want_hits=True, want_counts=True, adjudicate=True)
+    plan = dev.ScanPlan(dset, batch, thr, 3, out_rows, 2 * n, want_hits=True, want_counts=True, adjudicate=True,
+                        engine=args.engine)
     plan.launch()
     res0 = plan.finish(sort=True)  # calibrates the hit buffer; deterministic workload -> n_hits is fixed
     n_hits = res0.n_hits
@@ -208,15 +210,11 @@ def main():
         plan.counts.zero_()
         if ev:
             ev[1].record()
-        _lib.check(plan.lib.smg_scan(dset.handle, dev._ptr(batch.packed), dev._ptr(batch.amask), dev._ptr(batch.codes),
-                                     dev._ptr(batch.d_rows), batch.n_rows, dev._ptr(plan.d_out_rows), dev._ptr(plan.d_chunks),
-                                     plan.n_chunks, plan.chunk_len, plan.strands, dev._ptr(plan.d_lo), dev._ptr(plan.d_hi),
-                                     plan.pos_bits, plan.motif_bits, dev._ptr(plan.keys), dev._ptr(plan.scores), plan.hit_cap,
-                                     dev._ptr(plan.near), plan.near_cap, dev._ptr(plan.counts), dev._ptr(plan.counters),
-                                     dev._stream()), "smg_scan")
+        plan.launch_scan()
         if ev:
             ev[2].record()
-        plan.launch_adjudicate()
+        if plan.engine == "regtab":
+            plan.launch_adjudicate()
         dev.sort_hits(plan.keys, plan.scores, n_hits, plan.key_bits, keys_out, scores_out, sort_tmp)
         if world > 1:
             dist.all_gather_into_tensor(gathered, plan.counts)
@@ -264,7 +262,7 @@ def main():
         t0 = time.perf_counter()
         b2 = dev.SeqBatch(None, flat=(host_flat, src_off, lens))  # H2D + pack kernel (+ status readback)
         p2 = dev.ScanPlan(dset, b2, thr, 3, out_rows, 2 * n, hit_cap=plan.hit_cap, near_cap=plan.near_cap,
-                          chunk_len=plan.chunk_len)
+                          chunk_len=plan.chunk_len, engine=args.engine)
         p2.launch()
         r2 = p2.finish(sort=True)
         if world > 1:

@@ -146,7 +146,8 @@ def main():
         t_upload = time.perf_counter() - t0
         n = len(segs)
         out_rows = np.stack([np.zeros(n), np.ones(n)], axis=1).astype(np.int32)
-        plan = dev.ScanPlan(model.device_set, batch, model.thresholds(0.7), 3, out_rows, 2, want_hits=True, want_counts=True)
+        plan = dev.ScanPlan(model.device_set, batch, model.thresholds(0.7), 3, out_rows, 2, want_hits=True, want_counts=True,
+                            engine=os.environ.get("SMEAGOL_B200_ENGINE"))
         plan.launch()
         res = plan.finish(sort=False)
         total_counts = torch.zeros((1, M, 2), dtype=torch.int32, device=device)

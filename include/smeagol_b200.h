@@ -65,6 +65,7 @@ typedef struct {
 #define SMG_CTR_DEFINITE 2      /* hits decided by the fp32 kernel */
 #define SMG_CTR_ADJ_ACCEPTED 3  /* near-threshold candidates accepted by the fp64 adjudicator */
 #define SMG_CTR_LAUNCHES 4      /* kernel launches issued by the library on behalf of this counter block */
+#define SMG_CTR_CANDIDATES 5    /* smg_scan_tc: candidates emitted by the tensor-core prefilter (> cand_cap: overflow) */
 #define SMG_N_COUNTERS 8
 
 int smg_version(void);
@@ -76,6 +77,11 @@ uint64_t smg_launch_count(void);
  * concatenated row-major (sum(widths) x 4, columns A,C,G,T), HOST memory.  Builds the device tables: natural
  * layout, reverse-complement tables, and the lane-major register-table groups of the fused scan kernel. */
 int smg_pwmset_create(const float* h_weights, const int32_t* h_widths, int32_t n_motifs, smg_pwmset_t* out);
+/* Hybrid engine: PWMs narrower than tc_min_width (0 = no split, else 4*j+1) are scanned by smg_scan (register-table
+ * kernel), the others by smg_scan_tc (tensor-core prefilter + exact second pass); a complete scan calls both on the
+ * same hit / count / counter buffers.  With tc_min_width = 0 either entry point alone covers every PWM. */
+int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int32_t n_motifs, int32_t tc_min_width,
+                            smg_pwmset_t* out);
 int smg_pwmset_destroy(smg_pwmset_t set);
 /* info[0]=n_motifs info[1]=max_width info[2]=n_regtab_groups info[3]=n_buckets info[4]=n_wide_motifs
  * info[5]=sum over groups of padded width (dual groups count both strands) */
@@ -107,6 +113,20 @@ int smg_scan(smg_pwmset_t set, const uint32_t* d_packed, const uint16_t* d_amask
              int32_t n_chunks, int32_t chunk_len, int strands, const float* d_thr_lo, const float* d_thr_hi,
              int pos_bits, int motif_bits, uint64_t* d_hit_keys, float* d_hit_scores, uint64_t hit_cap,
              smg_near_t* d_near, uint64_t near_cap, int32_t* d_counts, uint64_t* d_counters, void* stream);
+
+/* Same contract and results as smg_scan + smg_adjudicate (hits, counts and counters are bit-identical), computed in two
+ * passes: (1) a tensor-core prefilter (mma.sync, fp16 weights x soft one-hot generated in registers, threshold on the
+ * accumulator fragment) emits every (row, start, motif, strand) whose approximate score exceeds d_thr_pre[motif]
+ * (the caller passes thr_lo minus a margin >= the fp16 error bound) into d_cand; (2) every candidate is re-scored in
+ * fp32 in the fixed summation order, the near-threshold band is adjudicated in fp64 against d_thr64, hits and counts
+ * are written.  candidate = row << (cand_pos_bits+motif_bits+1) | start << (motif_bits+1) | motif << 1 | strand.
+ * PWMs wider than SMG_MAX_REGTAB_WIDTH are not supported here (use smg_scan). */
+int smg_scan_tc(smg_pwmset_t set, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
+                const smg_row_t* d_rows, int32_t n_rows, const int32_t* d_out_rows, const smg_chunk_t* d_chunks,
+                int32_t n_chunks, int32_t chunk_len, int strands, const float* d_thr_lo, const float* d_thr_hi,
+                const float* d_thr_pre, const double* d_thr64, int pos_bits, int motif_bits, int cand_pos_bits,
+                uint64_t* d_cand, uint64_t cand_cap, uint64_t* d_hit_keys, float* d_hit_scores, uint64_t hit_cap,
+                int32_t* d_counts, uint64_t* d_counters, void* stream);
 
 /* fp64 adjudication of the near-threshold candidates: score64 = sum of the fp32 operands in double, hit iff
  * score64 > d_thr64[motif] (thr = frac * max_scores computed on the host as models.py:141 does). */

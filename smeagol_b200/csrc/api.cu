@@ -12,6 +12,9 @@
 #include "common.cuh"
 #include "launchers.h"
 #include "variant_regtab.cuh"
+#include "scan_hmma.cuh"
+#include "hmma_launchers.h"
+#include <cuda_fp16.h>
 #include "variant_launchers.h"
 
 // ------------------------------------------------------------------------------------------ host-side state
@@ -57,6 +60,15 @@ struct smg_pwmset {
     std::vector<Bucket> buckets;
     std::vector<int> wide;
     std::vector<int> dual_motifs, nondual_motifs;
+    // tensor-core prefilter: (PWM, strand) columns grouped by k16 steps KS = ceil(W / 4)
+    struct HmmaBucket { int ks, nb, first_colgroup, n_colgroups; };
+    std::vector<HmmaBucket> hbuckets;
+    int64_t n_hcols = 0;
+    int split = 0;  // > 0: smg_scan covers PWMs narrower than this, smg_scan_tc the others (hybrid engine)
+    uint32_t* d_afrag = nullptr;
+    int64_t* d_cg_afrag_off = nullptr;
+    int32_t* d_col_id = nullptr;
+    float* d_thr_pre_col = nullptr;
     int32_t* d_dual_list = nullptr;
     int32_t* d_nondual_list = nullptr;
     int64_t sum_padded = 0;
@@ -347,6 +359,81 @@ __global__ void __launch_bounds__(128) variant_windows_kernel(const ScanParams p
     }
 }
 
+// per-column prefilter thresholds of the tensor-core path (depend on the call's thresholds and strand mask)
+__global__ void hmma_thr_kernel(const int32_t* __restrict__ col_id, const float* __restrict__ thr_pre, const int strands,
+                                const int64_t n, float* __restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cid = col_id[i];
+    out[i] = (cid >= 0 && ((strands >> (cid & 1)) & 1)) ? thr_pre[cid >> 1] : __int_as_float(0x7f800000);
+}
+
+// Exact second pass of the tensor-core path: every candidate (row, start, motif, strand) emitted by the fp16 prefilter is
+// re-scored in fp32 in the register-table kernel's summation order, the near-threshold band is adjudicated in fp64,
+// and hits / counts are produced exactly as smg_scan + smg_adjudicate would.
+__global__ void __launch_bounds__(128) finalize_candidates_kernel(const ScanParams p, const unsigned long long* __restrict__ cand,
+                                                                  const unsigned long long cand_cap, const int cand_shift,
+                                                                  const double* __restrict__ thr64)
+{
+    const unsigned long long n_cand = min(p.counters[5], cand_cap);
+    const int key_shift = p.pos_bits + p.motif_bits;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long n_round = (n_cand + 31ull) & ~31ull;  // whole warps stay convergent for the ballots
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        bool hit = false;
+        float s32 = 0.f;
+        unsigned long long key = 0;
+        if (i < n_cand) {
+            const unsigned long long c = cand[i];
+            const int st = (int)(c & 1ull);
+            const int motif = (int)((c >> 1) & ((1ull << p.motif_bits) - 1ull));
+            const long long s = (long long)((c >> (p.motif_bits + 1)) & ((1ull << (cand_shift - p.motif_bits - 1)) - 1ull));
+            const int r = (int)(c >> cand_shift);
+            const smg_row_t row = p.rows[r];
+            const int wm = p.motif_width[motif];
+            const long long smax64 = row.g_len - row.g_off - (long long)wm;
+            if (s <= smax64 && ((p.strands >> st) & 1)) {
+                s32 = window_score32(p, row, motif, st, s);
+                if (s32 > p.thr_hi[motif]) {
+                    hit = true;
+                    atomicAdd(&p.counters[SMG_CTR_DEFINITE], 1ull);
+                } else if (s32 > p.thr_lo[motif]) {
+                    atomicAdd(&p.counters[SMG_CTR_NEAR], 1ull);
+                    const double s64 = window_score64(p.packed, p.amask, p.codes, row, p.nat_tab + p.motif_off[motif] * 4, wm, st,
+                                                      s, -1, 0);
+                    if (s64 > thr64[motif]) {
+                        hit = true;
+                        atomicAdd(&p.counters[SMG_CTR_ADJ_ACCEPTED], 1ull);
+                    }
+                }
+                if (hit) {
+                    if (p.counts) atomicAdd(p.counts + ((size_t)r * p.n_motifs + motif) * 2 + st, 1);
+                    const long long pos = st ? (smax64 - s) : (row.g_off + s);
+                    key = ((unsigned long long)(unsigned)p.out_rows[r * 2 + st] << key_shift) |
+                          ((unsigned long long)pos << p.motif_bits) | (unsigned long long)(unsigned)motif;
+                }
+            }
+        }
+        if (p.hit_keys) {
+            const unsigned m = __ballot_sync(SMG_FULL_MASK, hit);
+            if (m) {
+                unsigned long long base = 0;
+                if (lane == (unsigned)(__ffs((int)m) - 1)) base = atomicAdd(&p.counters[SMG_CTR_HITS_APPENDED], (unsigned long long)__popc(m));
+                base = __shfl_sync(SMG_FULL_MASK, base, __ffs((int)m) - 1);
+                if (hit) {
+                    const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+                    if (slot < p.hit_cap) {
+                        p.hit_keys[slot] = key;
+                        p.hit_scores[slot] = s32;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host helpers
 static int init_lut()
 {
@@ -384,11 +471,20 @@ uint64_t smg_launch_count(void) { return g_launches.load(); }
 
 int smg_pwmset_create(const float* h_weights, const int32_t* h_widths, int32_t n_motifs, smg_pwmset_t* out)
 {
+    return smg_pwmset_create_split(h_weights, h_widths, n_motifs, 0, out);
+}
+
+int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int32_t n_motifs, int32_t tc_min_width,
+                            smg_pwmset_t* out)
+{
     if (!h_weights || !h_widths || n_motifs <= 0 || !out) return fail(SMG_ERR_INVALID, "smg_pwmset_create: bad argument");
+    if (tc_min_width != 0 && (tc_min_width < 1 || (tc_min_width - 1) % 4 != 0))
+        return fail(SMG_ERR_INVALID, "smg_pwmset_create_split: tc_min_width must be 0 or 4*j + 1");
     int rc = init_lut();
     if (rc != SMG_OK) return rc;
     smg_pwmset* s = new smg_pwmset();
     s->n_motifs = n_motifs;
+    s->split = tc_min_width;
     s->widths.assign(h_widths, h_widths + n_motifs);
     s->offs.resize(n_motifs);
     int64_t tot = 0;
@@ -424,6 +520,9 @@ int smg_pwmset_create(const float* h_weights, const int32_t* h_widths, int32_t n
             if (any) last_w = w;
             const int nm = (std::max(w, 2) <= kPairMaxWidth) ? 2 : 1;
             while (pool.size() >= (size_t)32 * nm) emit_group(w, nm, (size_t)32 * nm);
+            // hybrid engine: lane groups never mix PWMs from both sides of the split
+            if (s->split > 0 && w == s->split - 1)
+                while (!pool.empty()) emit_group(last_w, 1, std::min(pool.size(), (size_t)32));
         }
         while (!pool.empty()) {
             const int nm = (std::max(last_w, 2) <= kPairMaxWidth && pool.size() > 32) ? 2 : 1;
@@ -471,6 +570,57 @@ int smg_pwmset_create(const float* h_weights, const int32_t* h_widths, int32_t n
             }
         }
     }
+    // ---- tensor-core prefilter tables: fp16 A fragments in mma.m16n8k16 register order
+    std::vector<uint32_t> afrag;
+    std::vector<int64_t> cg_off;
+    std::vector<int32_t> col_id;
+    {
+        #ifndef SMG_HMMA_NB_SMALL
+#define SMG_HMMA_NB_SMALL 4
+#endif
+        auto nb_for = [](int ks) { return ks <= 3 ? SMG_HMMA_NB_SMALL : ks == 4 ? (SMG_HMMA_NB_SMALL == 8 ? 6 : 4) : ks <= 6 ? 4 : 3; };
+        auto h16 = [](float v) { return (uint32_t)__half_as_ushort(__float2half_rn(v)); };
+        for (int ks = 1; ks <= SMG_MAX_REGTAB_WIDTH / 4; ++ks) {
+            std::vector<int> cols;  // motif * 2 + strand
+            for (int m = 0; m < n_motifs; ++m)
+                if ((h_widths[m] + 3) / 4 == ks) { cols.push_back(m * 2); cols.push_back(m * 2 + 1); }
+            if (cols.empty()) continue;
+            const int nb = nb_for(ks), per = nb * 16;
+            const int ncg = (int)((cols.size() + per - 1) / per);
+            // column groups of different buckets have different sizes: col arrays are indexed by colgroup * per within
+            // the bucket, so every bucket gets its own base such that (first_colgroup * per) is its first column
+            while ((int64_t)col_id.size() % per) col_id.push_back(-1);
+            const int first_cg = (int)(col_id.size() / per);
+            s->hbuckets.push_back({ks, nb, first_cg, ncg});
+            for (int cg = 0; cg < ncg; ++cg) {
+                while ((int64_t)cg_off.size() < first_cg + cg) cg_off.push_back(0);
+                cg_off.push_back((int64_t)afrag.size());
+                const size_t base = afrag.size();
+                afrag.resize(base + (size_t)nb * ks * 4 * 32, 0u);
+                for (int c = 0; c < per; ++c) {
+                    const size_t ci = (size_t)cg * per + c;
+                    const int cid = ci < cols.size() ? cols[ci] : -1;
+                    col_id.push_back(cid);
+                    if (cid < 0) continue;
+                    const int m = cid >> 1, st = cid & 1, wm = h_widths[m];
+                    const float* T = h_weights + s->offs[m] * 4;
+                    const int blk = c / 16, rrow = c % 16;
+                    for (int kstep = 0; kstep < ks; ++kstep)
+                        for (int kin = 0; kin < 16; ++kin) {
+                            const int k = kstep * 4 + kin / 4, b = kin % 4;  // PWM row, base
+                            float v = 0.f;
+                            if (k < wm) v = st ? T[(wm - 1 - k) * 4 + (3 - b)] : T[k * 4 + b];
+                            // fragment register r and lane holding (row rrow, k index kin)
+                            const int r = (rrow >= 8 ? 1 : 0) + (kin >= 8 ? 2 : 0);
+                            const int lane = (rrow % 8) * 4 + (kin % 8) / 2;
+                            uint32_t& reg = afrag[base + ((size_t)(blk * ks + kstep) * 4 + r) * 32 + lane];
+                            reg |= h16(v) << (16 * (kin & 1));
+                        }
+                }
+            }
+        }
+        s->n_hcols = (int64_t)col_id.size();
+    }
     std::vector<float> nat(h_weights, h_weights + tot * 4);
     std::vector<int32_t> wv(h_widths, h_widths + n_motifs);
     std::vector<int32_t> widev(s->wide.begin(), s->wide.end());
@@ -479,6 +629,8 @@ int smg_pwmset_create(const float* h_weights, const int32_t* h_widths, int32_t n
     if ((rc = upload(&s->d_nat, nat)) || (rc = upload(&s->d_width, wv)) || (rc = upload(&s->d_off, s->offs)) ||
         (rc = upload(&s->d_gtab, gtab)) || (rc = upload(&s->d_gtab_off, gtab_off)) ||
         (rc = upload(&s->d_lane_motif, lane_motif)) ||
+        (rc = upload(&s->d_afrag, afrag)) || (rc = upload(&s->d_cg_afrag_off, cg_off)) || (rc = upload(&s->d_col_id, col_id)) ||
+        (rc = upload(&s->d_thr_pre_col, std::vector<float>((size_t)std::max<int64_t>(s->n_hcols, 1), 0.f))) ||
         (rc = upload(&s->d_wide, widev)) || (rc = upload(&s->d_dual_list, dualv)) || (rc = upload(&s->d_nondual_list, nondualv))) {
         smg_pwmset_destroy(s);
         return rc;
@@ -491,7 +643,7 @@ int smg_pwmset_destroy(smg_pwmset_t s)
 {
     if (!s) return SMG_OK;
     cudaFree(s->d_nat); cudaFree(s->d_width); cudaFree(s->d_off); cudaFree(s->d_gtab); cudaFree(s->d_gtab_off);
-    cudaFree(s->d_lane_motif); cudaFree(s->d_wide); cudaFree(s->d_dual_list); cudaFree(s->d_nondual_list);
+    cudaFree(s->d_lane_motif); cudaFree(s->d_afrag); cudaFree(s->d_cg_afrag_off); cudaFree(s->d_col_id); cudaFree(s->d_thr_pre_col); cudaFree(s->d_wide); cudaFree(s->d_dual_list); cudaFree(s->d_nondual_list);
     delete s;
     return SMG_OK;
 }
@@ -558,6 +710,7 @@ int smg_scan(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amask, 
     SMG_CUDA(cudaEventRecord(pool->fork, st));
     int bi = 0;
     for (const Bucket& b : s->buckets) {
+        if (s->split > 0 && b.wb >= s->split) continue;  // the tensor-core engine owns these (smg_scan_tc)
         smg_launch_fn fn = smg_get_launcher(b.wb, b.nm);
         if (!fn) return fail(SMG_ERR_INVALID, "smg_scan: no kernel for padded width " + std::to_string(b.wb));
         cudaStream_t bs = (bi == 0) ? st : pool->side[(bi - 1) % StreamPool::kSide];
@@ -579,6 +732,65 @@ int smg_scan(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amask, 
         scan_wide_kernel<<<(unsigned)n_chunks, 128, 0, st>>>(p, s->d_wide, (int)s->wide.size());
         SMG_LAUNCH_CHECK("scan_wide_kernel");
     }
+    return SMG_OK;
+}
+
+int smg_scan_tc(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes, const smg_row_t* d_rows,
+                int32_t n_rows, const int32_t* d_out_rows, const smg_chunk_t* d_chunks, int32_t n_chunks, int32_t chunk_len,
+                int strands, const float* d_thr_lo, const float* d_thr_hi, const float* d_thr_pre, const double* d_thr64,
+                int pos_bits, int motif_bits, int cand_pos_bits, uint64_t* d_cand, uint64_t cand_cap, uint64_t* d_hit_keys,
+                float* d_hit_scores, uint64_t hit_cap, int32_t* d_counts, uint64_t* d_counters, void* stream)
+{
+    if (!s || !d_packed || !d_amask || !d_rows || n_rows <= 0 || !d_out_rows || !d_chunks || n_chunks < 0 || !d_thr_lo ||
+        !d_thr_hi || !d_thr_pre || !d_thr64 || !d_counters || !d_cand || cand_cap == 0)
+        return fail(SMG_ERR_INVALID, "smg_scan_tc: bad argument");
+    if (chunk_len <= 0 || (chunk_len & 15)) return fail(SMG_ERR_INVALID, "smg_scan_tc: chunk_len must be a positive multiple of 16");
+    if ((strands & 3) == 0 || (strands & ~3)) return fail(SMG_ERR_INVALID, "smg_scan_tc: strands must be 1, 2 or 3");
+    if (pos_bits <= 0 || motif_bits <= 0 || pos_bits + motif_bits > 63) return fail(SMG_ERR_INVALID, "smg_scan_tc: bad key layout");
+    if ((1ll << motif_bits) < s->n_motifs) return fail(SMG_ERR_INVALID, "smg_scan_tc: motif_bits too small");
+    if (cand_pos_bits <= 0 || cand_pos_bits + motif_bits + 1 > 62) return fail(SMG_ERR_INVALID, "smg_scan_tc: bad candidate layout");
+    if ((d_hit_keys == nullptr) != (d_hit_scores == nullptr)) return fail(SMG_ERR_INVALID, "smg_scan_tc: hit buffers must both be set or NULL");
+    if (n_chunks == 0) return SMG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    ScanParams p;
+    fill_params(p, s, d_packed, d_amask, d_codes, d_rows, d_out_rows);
+    p.chunks = d_chunks; p.chunk_len = chunk_len; p.strands = strands; p.thr_lo = d_thr_lo; p.thr_hi = d_thr_hi;
+    p.pos_bits = pos_bits; p.motif_bits = motif_bits;
+    p.hit_keys = reinterpret_cast<unsigned long long*>(d_hit_keys); p.hit_scores = d_hit_scores; p.hit_cap = hit_cap;
+    p.counts = d_counts; p.counters = reinterpret_cast<unsigned long long*>(d_counters);
+    if (s->n_hcols > 0) {
+        hmma_thr_kernel<<<(unsigned)((s->n_hcols + 255) / 256), 256, 0, st>>>(s->d_col_id, d_thr_pre, strands, s->n_hcols, s->d_thr_pre_col);
+        SMG_LAUNCH_CHECK("hmma_thr_kernel");
+    }
+    smg::HmmaParams hp;
+    hp.sp = p; hp.afrag = s->d_afrag; hp.cg_afrag_off = s->d_cg_afrag_off; hp.thr_pre_col = s->d_thr_pre_col; hp.col_id = s->d_col_id;
+    hp.cand_shift = cand_pos_bits + motif_bits + 1;
+    hp.cand = reinterpret_cast<unsigned long long*>(d_cand); hp.cand_cap = cand_cap;
+    StreamPool* pool = get_pool();
+    if (!pool) return fail(SMG_ERR_CUDA, "smg_scan_tc: cannot create the side streams");
+    SMG_CUDA(cudaEventRecord(pool->fork, st));
+    int bi = 0;
+    for (const smg_pwmset::HmmaBucket& b : s->hbuckets) {
+        if (s->split > 0 && 4 * b.ks < s->split) continue;  // the register-table engine owns these (smg_scan)
+        smg_hmma_launch_fn fn = smg_get_hmma_launcher(b.ks, b.nb);
+        if (!fn) return fail(SMG_ERR_INVALID, "smg_scan_tc: no kernel for KS " + std::to_string(b.ks));
+        cudaStream_t bs = (bi == 0) ? st : pool->side[(bi - 1) % StreamPool::kSide];
+        if (bi > 0 && bi <= StreamPool::kSide) SMG_CUDA(cudaStreamWaitEvent(bs, pool->fork, 0));
+        hp.first_colgroup = b.first_colgroup;
+        fn(hp, n_chunks, b.n_colgroups, bs);
+        SMG_LAUNCH_CHECK("scan_hmma_kernel");
+        ++bi;
+    }
+    const int used = std::min(std::max(bi - 1, 0), (int)StreamPool::kSide);
+    for (int i = 0; i < used; ++i) {
+        SMG_CUDA(cudaEventRecord(pool->join[i], pool->side[i]));
+        SMG_CUDA(cudaStreamWaitEvent(st, pool->join[i], 0));
+    }
+    // PWMs wider than the register / fragment kernels: emitted as candidates by a generic kernel? No -- scored directly.
+    if (!s->wide.empty() && s->split == 0) return fail(SMG_ERR_UNSUPPORTED, "smg_scan_tc: PWMs wider than 32 need smg_scan");
+    finalize_candidates_kernel<<<148 * 8, 128, 0, st>>>(p, reinterpret_cast<const unsigned long long*>(d_cand), cand_cap,
+                                                       hp.cand_shift, d_thr64);
+    SMG_LAUNCH_CHECK("finalize_candidates_kernel");
     return SMG_OK;
 }
 

@@ -1,0 +1,196 @@
+// Tensor-core PREFILTER for the PWM scan (the "im2col" variant of north_star, restated so that it stays exact).
+//
+// The window score is a contraction of a one-hot operand with the log-odds table:
+//     score[col][p] = sum_{k < W, b < 4} T_col[k][b] * X[p + k][b]            (models.py:50-68: Embedding + Conv1D)
+// i.e. a GEMM with M = (PWM, strand) columns, N = positions, K = 4 * W.  Here the WEIGHTS are the A operand and stay in
+// registers as fp16 fragments, the soft one-hot of the sequence is the B operand and is generated on the fly in
+// registers from the 2-bit packed bases (no shared-memory staging, no im2col buffer), and the accumulator fragment is
+// compared against the threshold IN REGISTERS -- which is why the legacy warp-level mma.sync is the right instruction:
+// a tcgen05 version has to read every accumulator back from TMEM (64 B/clk/SM = 16 cells/clk/SM), below what mma.sync
+// sustains for this K (951 MAC/clk/SM measured => 20-30 cells/clk/SM for W <= 12).
+//
+// fp16 weights cannot give the reference's fp32 scores, so this kernel is only a FILTER: it emits every cell whose
+// approximate score exceeds (threshold - margin), margin = 2^-9 * sum_k max_b |T[k][b]| (>= 4x the fp16 rounding error
+// of the operands), as a 64-bit candidate (row, start, motif, strand).  finalize_candidates_kernel (api.cu) then
+// re-scores each candidate in fp32 in the SAME fixed order as the register-table kernel, adjudicates the near-threshold
+// band in fp64, and produces hits / counts that are bit-identical to the register-table path.
+#pragma once
+#include "common.cuh"
+
+namespace smg {
+
+struct HmmaParams {
+    ScanParams sp;
+    const uint32_t* afrag;        // fp16x2 A fragments, per column group: [NB][KS][4][32]
+    const int64_t* cg_afrag_off;  // [n_colgroups] offset (in uint32) of each column group's fragments
+    const float* thr_pre_col;     // [n_colgroups * NB * 16] prefilter threshold per column (+inf for empty columns)
+    const int32_t* col_id;        // [n_colgroups * NB * 16] motif * 2 + strand, -1 for empty columns
+    int32_t first_colgroup;
+    int32_t cand_shift;           // candidate = row << cand_shift | start << (motif_bits + 1) | motif << 1 | strand
+    unsigned long long* cand;
+    unsigned long long cand_cap;
+};
+
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// fp16 pairs {e[c][bb], e[c][bb+1]} of the soft one-hot table (encode.py:11-29) for bb = 0 and bb = 2
+static __constant__ uint32_t c_emb16[17][2] = {
+    {0x00000000u, 0x00000000u},  // Z
+    {0x00003c00u, 0x00000000u},  // A
+    {0x3c000000u, 0x00000000u},  // C
+    {0x00000000u, 0x00003c00u},  // G
+    {0x00000000u, 0x3c000000u},  // T
+    {0x00000000u, 0x3c000000u},  // U
+    {0x34003400u, 0x34003400u},  // N  (0.25)
+    {0x00003800u, 0x38000000u},  // W  (A, T)
+    {0x38000000u, 0x00003800u},  // S  (C, G)
+    {0x38003800u, 0x00000000u},  // M  (A, C)
+    {0x00000000u, 0x38003800u},  // K  (G, T)
+    {0x00003800u, 0x00003800u},  // R  (A, G)
+    {0x38000000u, 0x38000000u},  // Y  (C, T)
+    {0x35550000u, 0x35553555u},  // B  (C, G, T) 1/3 = 0x3555
+    {0x00003555u, 0x35553555u},  // D  (A, G, T)
+    {0x35553555u, 0x35550000u},  // H  (A, C, T)
+    {0x35553555u, 0x00003555u},  // V  (A, C, G)
+};
+
+constexpr int kCandStage = 128;
+
+// KS = k16 steps (padded width = 4 * KS), NB = 16-column blocks per warp.  One warp per CTA; the warp walks its chunk
+// in tiles of 8 positions: B fragments for the next tile are generated (ALU) while the tensor pipe works on the
+// current one.
+template <int KS, int NB>
+__global__ void __launch_bounds__(32) scan_hmma_kernel(const HmmaParams hp)
+{
+    const ScanParams& p = hp.sp;
+    __shared__ unsigned long long s_cand[kCandStage];
+    const int lane = threadIdx.x;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int colgroup = hp.first_colgroup + blockIdx.y;
+    const smg_chunk_t ch = p.chunks[blockIdx.x];
+    const smg_row_t row = p.rows[ch.row];
+    const int c0 = ch.start;
+    const int c1 = min(c0 + p.chunk_len, row.n_own);
+    if (c1 <= c0) return;
+
+    // ---- weights: fp16 A fragments of NB x 16 columns in registers
+    uint32_t a[NB][KS][4];
+    {
+        const uint32_t* ga = hp.afrag + hp.cg_afrag_off[colgroup];
+#pragma unroll
+        for (int blk = 0; blk < NB; ++blk)
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) a[blk][ks][r] = ga[((blk * KS + ks) * 4 + r) * 32 + lane];
+    }
+    const int colbase = colgroup * (NB * 16);
+    float tA[NB], tB[NB];  // prefilter thresholds of the two columns this lane sees in each block
+#pragma unroll
+    for (int blk = 0; blk < NB; ++blk) {
+        tA[blk] = hp.thr_pre_col[colbase + blk * 16 + (lane >> 2)];
+        tB[blk] = hp.thr_pre_col[colbase + blk * 16 + (lane >> 2) + 8];
+    }
+    const int n = lane >> 2;         // position offset of this lane's B-fragment column within a tile
+    const int kk = (lane & 3) >> 1;  // PWM-row offset of its k-pair within a k16 slice (second register: +2)
+    const int bb = (lane & 1) * 2;   // its base pair {bb, bb+1}
+    const int q2 = (lane & 3) * 2;   // accumulator columns: positions pt + q2, pt + q2 + 1
+    const uint32_t* __restrict__ wp = p.packed + row.word_off;
+    const uint16_t* __restrict__ ap = p.amask + row.word_off;
+    const unsigned long long rowbits = (unsigned long long)(unsigned)ch.row << hp.cand_shift;
+    int nst = 0;
+
+    auto flush = [&]() {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&p.counters[SMG_CTR_CANDIDATES], (unsigned long long)nst);
+        base = __shfl_sync(SMG_FULL_MASK, base, 0);
+        for (int i = lane; i < nst; i += 32)
+            if (base + i < hp.cand_cap) hp.cand[base + i] = s_cand[i];
+        nst = 0;
+        __syncwarp();
+    };
+
+    // soft one-hot B fragments of the tile starting at pt (this lane: bases pt + n + 4*ks + kk (+2))
+    auto make_b = [&](const int pt, uint32_t (&b)[KS][2]) {
+        const int g = pt + n;
+        const int w0 = g >> 4, sh = 2 * (g & 15);
+        const unsigned long long lo = (unsigned long long)wp[w0] | ((unsigned long long)wp[w0 + 1] << 32);
+        const unsigned long long hi = (unsigned long long)wp[w0 + 2];
+        const unsigned long long win = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;  // 32 bases starting at g
+        // ambiguity mask of every base any lane of the warp touches in this tile: [pt, pt + 8 + 4*KS)
+        const int wt = pt >> 4;
+        const unsigned amb = (unsigned)ap[wt] | (unsigned)ap[wt + 1] | (unsigned)ap[wt + 2];
+        if (amb == 0u) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const unsigned d = ((unsigned)(win >> (2 * (4 * ks + kk + 2 * h))) & 3u) ^ (unsigned)bb;
+                    b[ks][h] = d < 2u ? (0x3c00u << (16 * d)) : 0u;
+                }
+            }
+        } else {  // IUPAC codes / 'Z' / padding somewhere near: soft one-hot from the code table
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int code = smg_fetch_code(p.packed, p.amask, p.codes, row, (long long)g + 4 * ks + kk + 2 * h);
+                    b[ks][h] = c_emb16[code][bb >> 1];
+                }
+            }
+        }
+    };
+
+    uint32_t b[KS][2];
+    make_b(c0, b);
+    for (int pt = c0; pt < c1; pt += 8) {
+        // ---- NB x KS tensor-core MMAs on the current tile, accumulators in registers
+        float c[NB][4];
+#pragma unroll
+        for (int blk = 0; blk < NB; ++blk) c[blk][0] = c[blk][1] = c[blk][2] = c[blk][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int blk = 0; blk < NB; ++blk) mma_f16(c[blk], a[blk][ks], b[ks][0], b[ks][1]);
+        // ---- B fragments of the next tile while the tensor pipe drains (rows are padded: reading ahead is safe)
+        make_b(pt + 8, b);
+        // ---- threshold in registers; candidates are rare: ballot + prefix-popcount compaction into the warp stage
+#pragma unroll
+        for (int blk = 0; blk < NB; ++blk) {
+            const float mA = fmaxf(c[blk][0], c[blk][1]), mB = fmaxf(c[blk][2], c[blk][3]);
+            if (__any_sync(SMG_FULL_MASK, (mA > tA[blk]) | (mB > tB[blk]))) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int s = pt + q2 + (i & 1);
+                    const bool cand = (c[blk][i] > ((i < 2) ? tA[blk] : tB[blk])) && (s < c1);
+                    const unsigned m = __ballot_sync(SMG_FULL_MASK, cand);
+                    if (m) {
+                        if (cand) {
+                            const int cid = hp.col_id[colbase + blk * 16 + (lane >> 2) + ((i < 2) ? 0 : 8)];
+                            s_cand[nst + __popc(m & lt_mask)] =
+                                rowbits | ((unsigned long long)(unsigned)s << (p.motif_bits + 1)) | (unsigned long long)(unsigned)cid;
+                        }
+                        nst += __popc(m);
+                        __syncwarp();
+                        if (nst > kCandStage - 32) flush();
+                    }
+                }
+            }
+        }
+    }
+    if (nst > 0) flush();
+}
+
+template <int KS, int NB>
+void launch_scan_hmma(const HmmaParams& hp, int n_chunks, int n_colgroups, cudaStream_t stream)
+{
+    dim3 grid((unsigned)n_chunks, (unsigned)n_colgroups, 1);
+    scan_hmma_kernel<KS, NB><<<grid, 32, 0, stream>>>(hp);
+}
+
+}  // namespace smg

@@ -4,6 +4,7 @@ Everything here talks to libsmeagol_b200.so through the C-ABI (smeagol_b200._lib
 memory, streams and (in dist.py) torch.distributed.  There is no CPU fallback.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -17,6 +18,8 @@ NEAR_DTYPE = np.dtype([("row", "<i4"), ("motif", "<i4"), ("strand", "<i4"), ("st
 ROW_PAD_BASES = 96  # every row is followed by at least this many 'Z' bases (halo + one prefetched word)
 NEAR_REL = 1e-5     # half-width of the near-threshold band, relative to sum_k max_b |T[k,b]|
 STRANDS = {"none": 1, "only": 2, "both": 3}
+DEFAULT_ENGINE = "regtab"
+DEFAULT_TC_MIN_WIDTH = 13  # measured on config c4: +6% over the register-table engine alone; no PWM of c1-c3, c5 is that wide
 
 
 def _require_cuda(device=None):
@@ -141,8 +144,13 @@ class DevicePWMSet:
     """Device tables of a PWM library (models.py:70-90 pads PWMs into one Conv1D kernel; here: natural fp32 tables,
     reverse-complement tables and lane-major register-table groups, built by smg_pwmset_create)."""
 
-    def __init__(self, weights, device=None):
+    def __init__(self, weights, device=None, tc_min_width=None):
+        """tc_min_width: PWMs at least this wide (4*j+1) go to the tensor-core engine, narrower ones to the
+        register-table engine (engine 'auto'); 0 = no split (either engine alone covers every PWM)."""
         self.device = _require_cuda(device)
+        if tc_min_width is None:
+            tc_min_width = int(os.environ.get("SMEAGOL_B200_TC_MIN_WIDTH", DEFAULT_TC_MIN_WIDTH))
+        self.tc_min_width = int(tc_min_width)
         lib = _lib.load()
         w32 = [np.ascontiguousarray(np.asarray(w), dtype=np.float32) for w in weights]
         for w in w32:
@@ -156,8 +164,9 @@ class DevicePWMSet:
         self.abs_scale = np.array([np.abs(w.astype(np.float64)).max(axis=1).sum() for w in w32])
         handle = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            _lib.check(lib.smg_pwmset_create(flat.ctypes.data_as(ctypes.c_void_p), self.widths.ctypes.data_as(ctypes.c_void_p),
-                                             self.n_motifs, ctypes.byref(handle)), "smg_pwmset_create")
+            _lib.check(lib.smg_pwmset_create_split(flat.ctypes.data_as(ctypes.c_void_p),
+                                                   self.widths.ctypes.data_as(ctypes.c_void_p), self.n_motifs,
+                                                   self.tc_min_width, ctypes.byref(handle)), "smg_pwmset_create_split")
         self.handle = handle
         info = (ctypes.c_int64 * 8)()
         _lib.check(lib.smg_pwmset_info(handle, info), "smg_pwmset_info")
@@ -255,8 +264,15 @@ class ScanPlan:
     """
 
     def __init__(self, pwmset, batch, thr64, strands, out_rows, n_out_rows, want_hits=True, want_counts=True,
-                 adjudicate=True, chunk_len=None, hit_cap=None, near_cap=None):
+                 adjudicate=True, chunk_len=None, hit_cap=None, near_cap=None, engine=None):
+        """engine: 'regtab' (fused FP32 register-table kernel) or 'hmma' (tensor-core prefilter + exact second pass;
+        same results).  Default: $SMEAGOL_B200_ENGINE or DEFAULT_ENGINE."""
         self.lib = _lib.load()
+        self.engine = engine or os.environ.get("SMEAGOL_B200_ENGINE", DEFAULT_ENGINE)
+        if pwmset.tc_min_width > 0:
+            self.engine = "auto"    # the PWM set was built split: both engines run, each on its side
+        elif self.engine == "auto" or (self.engine == "hmma" and pwmset.n_wide > 0):
+            self.engine = "regtab"  # PWMs wider than 32 only exist in the register-table / generic path
         self.pwmset, self.batch = pwmset, batch
         dev = batch.device
         M = pwmset.n_motifs
@@ -285,6 +301,15 @@ class ScanPlan:
         self.near_cap = (1 << 16) if near_cap is None else int(near_cap)
         self.counts = torch.zeros((batch.n_rows, M, 2), dtype=torch.int32, device=dev) if want_counts else None
         self.counters = torch.zeros(_lib.N_COUNTERS, dtype=torch.int64, device=dev)
+        self.cand_cap = 0
+        if self.engine in ("hmma", "auto"):
+            # prefilter bound: below thr_lo by 2^-9 * sum_k max_b |T| (>= 4x the fp16 rounding error of the operands)
+            pre = _round_down_f32(lo.astype(np.float64) - 2.0 ** -9 * np.asarray(pwmset.abs_scale, dtype=np.float64) - 1e-30)
+            self.d_pre = torch.from_numpy(pre).to(dev)
+            self.cand_pos_bits = _bits(int(batch.rows_host["n_avail"].max()) + 2)
+            if self.cand_pos_bits + self.motif_bits + 1 + _bits(batch.n_rows) > 62:
+                raise ValueError("candidate key does not fit in 62 bits")
+            self.cand_cap = int(self.hit_cap * 1.25) + 4096
         self._alloc()
 
     def _alloc(self):
@@ -292,23 +317,44 @@ class ScanPlan:
         self.keys = torch.empty(self.hit_cap, dtype=torch.int64, device=dev) if self.want_hits else None
         self.scores = torch.empty(self.hit_cap, dtype=torch.float32, device=dev) if self.want_hits else None
         self.near = torch.empty(self.near_cap * _lib.NEAR_BYTES, dtype=torch.uint8, device=dev)
+        self.cand = torch.empty(self.cand_cap, dtype=torch.int64, device=dev) if self.engine in ("hmma", "auto") else None
 
     @property
     def key_bits(self):
         return self.motif_bits + self.pos_bits + self.row_bits
 
     def launch(self):
-        b, lib = self.batch, self.lib
         self.counters.zero_()
         if self.counts is not None:
             self.counts.zero_()
+        self.launch_scan()
+        if self.engine == "regtab" and self.adjudicate:
+            self.launch_adjudicate()
+
+    def launch_scan(self):
+        """Enqueue the scan kernels only (the tensor-core engine's exact second pass includes the adjudication)."""
+        b, lib = self.batch, self.lib
+        if self.engine == "auto":  # register-table side (+ its adjudication), then the tensor-core side
+            self._launch_regtab()
+            if self.adjudicate:
+                self.launch_adjudicate()
+        if self.engine in ("hmma", "auto"):
+            _lib.check(lib.smg_scan_tc(self.pwmset.handle, _ptr(b.packed), _ptr(b.amask), _ptr(b.codes), _ptr(b.d_rows), b.n_rows,
+                                       _ptr(self.d_out_rows), _ptr(self.d_chunks), self.n_chunks, self.chunk_len, self.strands,
+                                       _ptr(self.d_lo), _ptr(self.d_hi), _ptr(self.d_pre), _ptr(self.d_thr), self.pos_bits,
+                                       self.motif_bits, self.cand_pos_bits, _ptr(self.cand), self.cand_cap, _ptr(self.keys),
+                                       _ptr(self.scores), self.hit_cap, _ptr(self.counts), _ptr(self.counters), _stream()),
+                       "smg_scan_tc")
+            return
+        self._launch_regtab()
+
+    def _launch_regtab(self):
+        b, lib = self.batch, self.lib
         _lib.check(lib.smg_scan(self.pwmset.handle, _ptr(b.packed), _ptr(b.amask), _ptr(b.codes), _ptr(b.d_rows), b.n_rows,
                                 _ptr(self.d_out_rows), _ptr(self.d_chunks), self.n_chunks, self.chunk_len, self.strands,
                                 _ptr(self.d_lo), _ptr(self.d_hi), self.pos_bits, self.motif_bits, _ptr(self.keys),
                                 _ptr(self.scores), self.hit_cap, _ptr(self.near), self.near_cap, _ptr(self.counts),
                                 _ptr(self.counters), _stream()), "smg_scan")
-        if self.adjudicate:
-            self.launch_adjudicate()
 
     def launch_adjudicate(self):
         b, lib = self.batch, self.lib
@@ -328,6 +374,9 @@ class ScanPlan:
             if self.want_hits and n_app > self.hit_cap:
                 self.hit_cap = int(n_app * 1.1) + 1024
                 grow = True
+            if self.engine in ("hmma", "auto") and int(c[_lib.CTR_CANDIDATES]) > self.cand_cap:
+                self.cand_cap = int(int(c[_lib.CTR_CANDIDATES]) * 1.1) + 1024
+                grow = True
             if not grow:
                 break
             self._alloc()
@@ -336,7 +385,8 @@ class ScanPlan:
         stats = {"n_definite": int(c[_lib.CTR_DEFINITE]), "n_near": n_near,
                  "n_adjudicated_accepted": int(c[_lib.CTR_ADJ_ACCEPTED]),
                  "n_hits_total": int(c[_lib.CTR_DEFINITE]) + int(c[_lib.CTR_ADJ_ACCEPTED]), "chunk_len": self.chunk_len,
-                 "n_chunks": self.n_chunks, "hit_cap": self.hit_cap, "near_cap": self.near_cap}
+                 "n_chunks": self.n_chunks, "hit_cap": self.hit_cap, "near_cap": self.near_cap, "engine": self.engine,
+                 "n_candidates": int(c[_lib.CTR_CANDIDATES])}
         keys, scores = self.keys, self.scores
         if self.want_hits and sort and n_hits > 0:
             keys, scores = sort_hits(keys, scores, n_hits, self.key_bits)
@@ -344,7 +394,7 @@ class ScanPlan:
 
 
 def scan(pwmset, batch, thr64, strands, out_rows, n_out_rows, want_hits=True, want_counts=True, adjudicate=True,
-         chunk_len=None, hit_cap=None, near_cap=None, sort=True):
+         chunk_len=None, hit_cap=None, near_cap=None, sort=True, engine=None):
     """Fused two-strand scan of a SeqBatch against a DevicePWMSet.
 
     thr64: per-PWM thresholds (frac * max_scores, computed by the caller exactly as models.py:141 does).
@@ -352,7 +402,7 @@ def scan(pwmset, batch, thr64, strands, out_rows, n_out_rows, want_hits=True, wa
     Returns a ScanResult.  Hit-buffer overflow is detected and the scan retried with a larger buffer, never truncated.
     """
     plan = ScanPlan(pwmset, batch, thr64, strands, out_rows, n_out_rows, want_hits, want_counts, adjudicate, chunk_len,
-                    hit_cap, near_cap)
+                    hit_cap, near_cap, engine)
     plan.launch()
     return plan.finish(sort=sort)
 

@@ -21,7 +21,7 @@ class PWMModel:
     `(double)score_f32 > thr` compare (models.py:108).
     """
 
-    def __init__(self, pwm_df, adjudicate=True):
+    def __init__(self, pwm_df, adjudicate=True, tc_min_width=None):
         self.Matrix_ids = np.array(pwm_df.Matrix_id)
         self.weights = [np.asarray(w) for w in pwm_df.weights]
         self.widths = np.array([w.shape[0] for w in self.weights])
@@ -30,6 +30,7 @@ class PWMModel:
         self.channels = len(self.weights)
         self.max_width = max(self.widths)
         self.adjudicate = adjudicate
+        self.tc_min_width = tc_min_width  # hybrid engine split (device.DevicePWMSet), None = library default
         self._dev = None
         self.last_scan_stats = None
 
@@ -37,7 +38,7 @@ class PWMModel:
     @property
     def device_set(self):
         if self._dev is None:
-            self._dev = dev.DevicePWMSet(self.weights)
+            self._dev = dev.DevicePWMSet(self.weights, tc_min_width=self.tc_min_width)
         return self._dev
 
     def thresholds(self, frac_threshold):

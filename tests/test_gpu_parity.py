@@ -38,6 +38,9 @@ def rand_seq(rng, L, alphabet="ACGT", p=None):
     return "".join(rng.choice(list(alphabet), size=L, p=p))
 
 
+ENGINE = None  # set by the engine-parametrised tests
+
+
 def device_scan(model, seqs, frac, rcomp="both", chunk_len=None, segments=None, adjudicate=True):
     """Scan forward strings as ONE group -> (row, pos, motif, score) with rows [fwd..., rc...] like the oracle."""
     from smeagol_b200 import device as dev
@@ -51,7 +54,7 @@ def device_scan(model, seqs, frac, rcomp="both", chunk_len=None, segments=None, 
     else:
         out_rows = np.stack([np.arange(n), n + np.arange(n)], axis=1)
     res = dev.scan(model.device_set, batch, model.thresholds(frac), dev.STRANDS[rcomp], out_rows.astype(np.int32),
-                   2 * n if rcomp == "both" else n, adjudicate=adjudicate, chunk_len=chunk_len)
+                   2 * n if rcomp == "both" else n, adjudicate=adjudicate, chunk_len=chunk_len, engine=ENGINE)
     return res
 
 
@@ -427,3 +430,60 @@ def test_edge_inputs():
                                model, 0.5, group_by="name")
     with pytest.raises(AssertionError):
         sb.scan.scan_sequences(recs, model, 1.5)
+
+
+@pytest.fixture
+def hmma_engine():
+    global ENGINE
+    ENGINE = "hmma"
+    yield
+    ENGINE = None
+
+
+def test_tensor_core_engine_bit_identical(hmma_engine):
+    """The tensor-core prefilter + exact second pass must give the same hits, fp32 scores and counts as the oracle
+    (and hence as the register-table engine): widths 1..32, IUPAC codes, every rcomp mode, chunk boundaries."""
+    sb = _sb()
+    rng = np.random.default_rng(41)
+    ws = []
+    for W in list(range(1, 33)) * 2:
+        ppm = (rng.dirichlet([0.5] * 4, size=W) + 0.01) / 1.04
+        ws.append(np.log2(ppm / 0.25))
+    model = sb.models.PWMModel(pd.DataFrame({"Matrix_id": ["W%02d_%d" % (w.shape[0], i) for i, w in enumerate(ws)],
+                                             "weights": ws}), tc_min_width=0)
+    amb = "ACGTNWSMKRYBDHVZ"
+    pa = np.array([0.23] * 4 + [0.08 / 12] * 12)
+    seqs = [rand_seq(rng, 1500), rand_seq(rng, 777, amb, pa / pa.sum()), rand_seq(rng, 31), "ACGTA", ""]
+    res, exp = check_against_oracle(model, seqs, 0.55, "both", chunk_len=256)
+    assert res.stats["engine"] == "hmma" and res.stats["n_candidates"] >= len(exp["row"])
+    check_against_oracle(model, seqs, 0.55, "none", chunk_len=4096)
+    check_against_oracle(model, seqs, 0.55, "only", chunk_len=256)
+    model2 = sb.models.PWMModel(synth_pwms(rng, 150, 5, 24), tc_min_width=0)
+    check_against_oracle(model2, [rand_seq(rng, 3000), "N" * 300 + rand_seq(rng, 500) + "N" * 100], 0.6, "both", chunk_len=512)
+    check_against_oracle(model2, [rand_seq(rng, 900)], 1.0, "both")
+    check_against_oracle(model2, [rand_seq(rng, 900)], 0.2, "both", atol=1e-5)
+
+
+def test_hybrid_engine_split_bit_identical():
+    """Hybrid engine: PWMs narrower than the split on the register-table kernel, the others on the tensor-core
+    prefilter + exact second pass, both writing the same hit / count buffers -- results identical to the oracle."""
+    sb = _sb()
+    rng = np.random.default_rng(43)
+    ws = []
+    for W in list(range(1, 41)) * 2:  # includes PWMs wider than 32 (generic kernel on the smg_scan side)
+        ppm = (rng.dirichlet([0.5] * 4, size=W) + 0.01) / 1.04
+        ws.append(np.log2(ppm / 0.25))
+    df = pd.DataFrame({"Matrix_id": ["W%02d_%d" % (w.shape[0], i) for i, w in enumerate(ws)], "weights": ws})
+    amb = "ACGTNWSMKRYBDHVZ"
+    pa = np.array([0.23] * 4 + [0.08 / 12] * 12)
+    seqs = [rand_seq(rng, 1500), rand_seq(rng, 777, amb, pa / pa.sum()), rand_seq(rng, 31), ""]
+    for split in (5, 13, 21):
+        model = sb.models.PWMModel(df, tc_min_width=split)
+        res, exp = check_against_oracle(model, seqs, 0.55, "both", chunk_len=256)
+        assert res.stats["engine"] == "auto"
+        if split == 5:
+            assert res.stats["n_candidates"] > 0  # the tensor-core side really ran
+        check_against_oracle(model, seqs, 0.55, "only", chunk_len=4096)
+    plain = sb.models.PWMModel(df, tc_min_width=0)
+    res, _ = check_against_oracle(plain, seqs, 0.55, "both")
+    assert res.stats["engine"] == "regtab"

@@ -22,7 +22,7 @@ out_rows = np.array([[0, 1]], dtype=np.int32)
 for W in widths:
     pw = synth.synth_pwms(nm, widths=[W] * nm)
     model = PWMModel(pw)
-    plan = dev.ScanPlan(model.device_set, batch, model.thresholds(frac), 3, out_rows, 2)
+    plan = dev.ScanPlan(model.device_set, batch, model.thresholds(frac), 3, out_rows, 2, engine=os.environ.get("SMEAGOL_B200_ENGINE"))
     plan.launch()
     res = plan.finish(sort=False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -31,12 +31,7 @@ for W in widths:
         plan.counters.zero_()
         plan.counts.zero_()
         e0.record()
-        _lib.check(plan.lib.smg_scan(model.device_set.handle, dev._ptr(batch.packed), dev._ptr(batch.amask), dev._ptr(batch.codes),
-                                     dev._ptr(batch.d_rows), batch.n_rows, dev._ptr(plan.d_out_rows), dev._ptr(plan.d_chunks),
-                                     plan.n_chunks, plan.chunk_len, plan.strands, dev._ptr(plan.d_lo), dev._ptr(plan.d_hi),
-                                     plan.pos_bits, plan.motif_bits, dev._ptr(plan.keys), dev._ptr(plan.scores), plan.hit_cap,
-                                     dev._ptr(plan.near), plan.near_cap, dev._ptr(plan.counts), dev._ptr(plan.counters),
-                                     dev._stream()), "smg_scan")
+        plan.launch_scan()
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
