@@ -196,6 +196,35 @@ __device__ float window_score32(const ScanParams& p, const smg_row_t& row, const
     return acc;
 }
 
+// Same value as window_score32 (bit for bit) for a window of plain A/C/G/T bases that lies inside the row, W <= 32:
+// the bases come from three packed words held in registers, one table load + one add per PWM row.  Returns false when
+// the window needs the general path (ambiguity codes, 'Z', end padding, wider PWM).
+__device__ __forceinline__ bool window_score32_acgt(const ScanParams& p, const smg_row_t& row, const int motif, const int st,
+                                                    const int64_t s, float* out)
+{
+    const int wm = p.motif_width[motif];
+    if (wm > 32 || s < 0 || s + wm > row.n_avail) return false;
+    const int64_t w0 = row.word_off + (s >> 4);
+    if ((p.amask[w0] | p.amask[w0 + 1] | p.amask[w0 + 2]) != 0) return false;  // rows are padded: w0 + 2 is allocated
+    const int sh = 2 * (int)(s & 15);
+    const unsigned long long lo = (unsigned long long)p.packed[w0] | ((unsigned long long)p.packed[w0 + 1] << 32);
+    const unsigned long long hi = (unsigned long long)p.packed[w0 + 2];
+    unsigned long long win = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
+    const float* tab = p.nat_tab + p.motif_off[motif] * 4;
+    const int last = 4 * wm - 1;
+    // forward: T[k][b]; reverse complement on the forward string: T[W-1-k][3-b] = flat index (4W-1) - (4k+b).
+    // Ascending k, one rounded add per row: the summation order of the register-table kernel's ACGT path.
+    float acc = 0.f;
+    for (int k = 0; k < wm; ++k) {
+        const int j = 4 * k + (int)(win & 3ull);
+        win >>= 2;
+        const float term = tab[st ? (last - j) : j];
+        acc = (k == 0) ? term : __fadd_rn(acc, term);
+    }
+    *out = acc;
+    return true;
+}
+
 __device__ double window_score64(const uint32_t* packed, const uint16_t* amask, const uint8_t* codes, const smg_row_t& row,
                                  const float* tab, const int wm, const int st, const int64_t s, const int64_t sub_pos,
                                  const int sub_code)
@@ -372,14 +401,15 @@ __global__ void hmma_thr_kernel(const int32_t* __restrict__ col_id, const float*
 // Exact second pass of the tensor-core path: every candidate (row, start, motif, strand) emitted by the fp16 prefilter is
 // re-scored in fp32 in the register-table kernel's summation order, the near-threshold band is adjudicated in fp64,
 // and hits / counts are produced exactly as smg_scan + smg_adjudicate would.
-__global__ void __launch_bounds__(128) finalize_candidates_kernel(const ScanParams p, const unsigned long long* __restrict__ cand,
+__global__ void __launch_bounds__(256) finalize_candidates_kernel(const ScanParams p, const unsigned long long* __restrict__ cand,
                                                                   const unsigned long long cand_cap, const int cand_shift,
                                                                   const double* __restrict__ thr64)
 {
-    const unsigned long long n_cand = min(p.counters[5], cand_cap);
+    const unsigned long long n_cand = min(p.counters[SMG_CTR_CANDIDATES], cand_cap);
     const int key_shift = p.pos_bits + p.motif_bits;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long n_round = (n_cand + 31ull) & ~31ull;  // whole warps stay convergent for the ballots
+    unsigned n_def = 0, n_near = 0, n_acc = 0;                      // per-thread tallies, one atomic per warp at the end
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         bool hit = false;
@@ -395,17 +425,17 @@ __global__ void __launch_bounds__(128) finalize_candidates_kernel(const ScanPara
             const int wm = p.motif_width[motif];
             const long long smax64 = row.g_len - row.g_off - (long long)wm;
             if (s <= smax64 && ((p.strands >> st) & 1)) {
-                s32 = window_score32(p, row, motif, st, s);
+                if (!window_score32_acgt(p, row, motif, st, s, &s32)) s32 = window_score32(p, row, motif, st, s);
                 if (s32 > p.thr_hi[motif]) {
                     hit = true;
-                    atomicAdd(&p.counters[SMG_CTR_DEFINITE], 1ull);
+                    ++n_def;
                 } else if (s32 > p.thr_lo[motif]) {
-                    atomicAdd(&p.counters[SMG_CTR_NEAR], 1ull);
+                    ++n_near;
                     const double s64 = window_score64(p.packed, p.amask, p.codes, row, p.nat_tab + p.motif_off[motif] * 4, wm, st,
                                                       s, -1, 0);
                     if (s64 > thr64[motif]) {
                         hit = true;
-                        atomicAdd(&p.counters[SMG_CTR_ADJ_ACCEPTED], 1ull);
+                        ++n_acc;
                     }
                 }
                 if (hit) {
@@ -431,6 +461,14 @@ __global__ void __launch_bounds__(128) finalize_candidates_kernel(const ScanPara
                 }
             }
         }
+    }
+    n_def = __reduce_add_sync(SMG_FULL_MASK, n_def);
+    n_near = __reduce_add_sync(SMG_FULL_MASK, n_near);
+    n_acc = __reduce_add_sync(SMG_FULL_MASK, n_acc);
+    if (lane == 0) {
+        if (n_def) atomicAdd(&p.counters[SMG_CTR_DEFINITE], (unsigned long long)n_def);
+        if (n_near) atomicAdd(&p.counters[SMG_CTR_NEAR], (unsigned long long)n_near);
+        if (n_acc) atomicAdd(&p.counters[SMG_CTR_ADJ_ACCEPTED], (unsigned long long)n_acc);
     }
 }
 
@@ -751,6 +789,11 @@ int smg_scan_tc(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amas
     if (cand_pos_bits <= 0 || cand_pos_bits + motif_bits + 1 > 62) return fail(SMG_ERR_INVALID, "smg_scan_tc: bad candidate layout");
     if ((d_hit_keys == nullptr) != (d_hit_scores == nullptr)) return fail(SMG_ERR_INVALID, "smg_scan_tc: hit buffers must both be set or NULL");
     if (n_chunks == 0) return SMG_OK;
+    {   // nothing on the tensor-core side of the split (e.g. no PWM that wide in the set): no launches at all
+        bool any = false;
+        for (const smg_pwmset::HmmaBucket& b : s->hbuckets) any = any || !(s->split > 0 && 4 * b.ks < s->split);
+        if (!any && (s->wide.empty() || s->split > 0)) return SMG_OK;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     ScanParams p;
     fill_params(p, s, d_packed, d_amask, d_codes, d_rows, d_out_rows);
@@ -788,7 +831,7 @@ int smg_scan_tc(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amas
     }
     // PWMs wider than the register / fragment kernels: emitted as candidates by a generic kernel? No -- scored directly.
     if (!s->wide.empty() && s->split == 0) return fail(SMG_ERR_UNSUPPORTED, "smg_scan_tc: PWMs wider than 32 need smg_scan");
-    finalize_candidates_kernel<<<148 * 8, 128, 0, st>>>(p, reinterpret_cast<const unsigned long long*>(d_cand), cand_cap,
+    finalize_candidates_kernel<<<148 * 8, 256, 0, st>>>(p, reinterpret_cast<const unsigned long long*>(d_cand), cand_cap,
                                                        hp.cand_shift, d_thr64);
     SMG_LAUNCH_CHECK("finalize_candidates_kernel");
     return SMG_OK;

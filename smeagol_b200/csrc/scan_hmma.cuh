@@ -38,6 +38,22 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], c
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// first k16 slice of a tile: accumulate onto zero (the zero operand is RZ, no accumulator initialisation needed)
+__device__ __forceinline__ void mma_f16_zero(float (&c)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+
+// 0x3c00 (fp16 1.0) shifted left by s; PTX shl clamps shift amounts above 31, i.e. s >= 32 gives 0
+__device__ __forceinline__ uint32_t shl_one_f16(const uint32_t s)
+{
+    uint32_t d;
+    asm("shl.b32 %0, 0x3c00, %1;" : "=r"(d) : "r"(s));
+    return d;
+}
+
 // fp16 pairs {e[c][bb], e[c][bb+1]} of the soft one-hot table (encode.py:11-29) for bb = 0 and bb = 2
 static __constant__ uint32_t c_emb16[17][2] = {
     {0x00000000u, 0x00000000u},  // Z
@@ -126,12 +142,23 @@ __global__ void __launch_bounds__(32) scan_hmma_kernel(const HmmaParams hp)
         const int wt = pt >> 4;
         const unsigned amb = (unsigned)ap[wt] | (unsigned)ap[wt + 1] | (unsigned)ap[wt + 2];
         if (amb == 0u) {
+            // d = base ^ bb selects the half of the fp16 pair that is 1.0 (d = 0: low, 1: high, 2 and 3: neither):
+            // value = 0x3c00 << (16 * d) with the shift clamped, 16 * d taken straight from the window bits.
+            // Three instructions per fragment register (shift, and-xor, shift) after one per-lane pre-shift by kk.
+            const uint32_t lo32 = (uint32_t)win, hi32 = (uint32_t)(win >> 32);
+            const uint32_t klo = __funnelshift_r(lo32, hi32, 2 * kk), khi = hi32 >> (2 * kk);
+            const uint32_t bb16 = (uint32_t)bb << 4;  // 16 * bb
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const unsigned d = ((unsigned)(win >> (2 * (4 * ks + kk + 2 * h))) & 3u) ^ (unsigned)bb;
-                    b[ks][h] = d < 2u ? (0x3c00u << (16 * d)) : 0u;
+                    const int bit = 2 * (4 * ks + 2 * h);  // bit offset of this row's base in the pre-shifted window
+                    uint32_t x;                            // 2-bit base code moved to bits 4..5 (fields never straddle)
+                    if (bit == 0) x = klo << 4;
+                    else if (bit < 32) x = klo >> (bit - 4);
+                    else if (bit == 32) x = khi << 4;
+                    else x = khi >> (bit - 36);
+                    b[ks][h] = shl_one_f16((x & 0x30u) ^ bb16);
                 }
             }
         } else {  // IUPAC codes / 'Z' / padding somewhere near: soft one-hot from the code table
@@ -149,35 +176,40 @@ __global__ void __launch_bounds__(32) scan_hmma_kernel(const HmmaParams hp)
     uint32_t b[KS][2];
     make_b(c0, b);
     for (int pt = c0; pt < c1; pt += 8) {
-        // ---- NB x KS tensor-core MMAs on the current tile, accumulators in registers
         float c[NB][4];
-#pragma unroll
-        for (int blk = 0; blk < NB; ++blk) c[blk][0] = c[blk][1] = c[blk][2] = c[blk][3] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
-            for (int blk = 0; blk < NB; ++blk) mma_f16(c[blk], a[blk][ks], b[ks][0], b[ks][1]);
-        // ---- B fragments of the next tile while the tensor pipe drains (rows are padded: reading ahead is safe)
-        make_b(pt + 8, b);
-        // ---- threshold in registers; candidates are rare: ballot + prefix-popcount compaction into the warp stage
+            for (int blk = 0; blk < NB; ++blk) {
+                if (ks == 0) mma_f16_zero(c[blk], a[blk][ks], b[ks][0], b[ks][1]);
+                else mma_f16(c[blk], a[blk][ks], b[ks][0], b[ks][1]);
+            }
+        make_b(pt + 8, b);  // next tile (ALU) while the tensor pipe drains this one; rows are padded: reading ahead is safe
+        // one vote for the whole tile (NB x 16 columns x 8 positions), then per block only when something passed
+        bool any = false;
 #pragma unroll
-        for (int blk = 0; blk < NB; ++blk) {
-            const float mA = fmaxf(c[blk][0], c[blk][1]), mB = fmaxf(c[blk][2], c[blk][3]);
-            if (__any_sync(SMG_FULL_MASK, (mA > tA[blk]) | (mB > tB[blk]))) {
+        for (int blk = 0; blk < NB; ++blk)
+            any = any || (fmaxf(c[blk][0], c[blk][1]) > tA[blk]) || (fmaxf(c[blk][2], c[blk][3]) > tB[blk]);
+        if (__any_sync(SMG_FULL_MASK, any)) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int s = pt + q2 + (i & 1);
-                    const bool cand = (c[blk][i] > ((i < 2) ? tA[blk] : tB[blk])) && (s < c1);
-                    const unsigned m = __ballot_sync(SMG_FULL_MASK, cand);
-                    if (m) {
-                        if (cand) {
-                            const int cid = hp.col_id[colbase + blk * 16 + (lane >> 2) + ((i < 2) ? 0 : 8)];
-                            s_cand[nst + __popc(m & lt_mask)] =
-                                rowbits | ((unsigned long long)(unsigned)s << (p.motif_bits + 1)) | (unsigned long long)(unsigned)cid;
+            for (int blk = 0; blk < NB; ++blk) {
+                const float mA = fmaxf(c[blk][0], c[blk][1]), mB = fmaxf(c[blk][2], c[blk][3]);
+                if (__any_sync(SMG_FULL_MASK, (mA > tA[blk]) | (mB > tB[blk]))) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int s = pt + q2 + (i & 1);
+                        const bool cand = (c[blk][i] > ((i < 2) ? tA[blk] : tB[blk])) && (s < c1);
+                        const unsigned m = __ballot_sync(SMG_FULL_MASK, cand);
+                        if (m) {
+                            if (cand) {
+                                const int cid = hp.col_id[colbase + blk * 16 + (lane >> 2) + ((i < 2) ? 0 : 8)];
+                                s_cand[nst + __popc(m & lt_mask)] =
+                                    rowbits | ((unsigned long long)(unsigned)s << (p.motif_bits + 1)) | (unsigned long long)(unsigned)cid;
+                            }
+                            nst += __popc(m);
+                            __syncwarp();
+                            if (nst > kCandStage - 32) flush();
                         }
-                        nst += __popc(m);
-                        __syncwarp();
-                        if (nst > kCandStage - 32) flush();
                     }
                 }
             }

@@ -19,7 +19,7 @@ ROW_PAD_BASES = 96  # every row is followed by at least this many 'Z' bases (hal
 NEAR_REL = 1e-5     # half-width of the near-threshold band, relative to sum_k max_b |T[k,b]|
 STRANDS = {"none": 1, "only": 2, "both": 3}
 DEFAULT_ENGINE = "regtab"
-DEFAULT_TC_MIN_WIDTH = 13  # measured on config c4: +6% over the register-table engine alone; no PWM of c1-c3, c5 is that wide
+DEFAULT_TC_MIN_WIDTH = 9  # measured: c2 1028 vs 960, c3 1206 vs 1127, c4 1259 vs 1184 Gbase*motif/s against a split at 13 (tools/sweep_split.sh)
 
 
 def _require_cuda(device=None):
