@@ -46,6 +46,22 @@ __device__ __forceinline__ void mma_f16_zero(float (&c)[4], const uint32_t (&a)[
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
 }
 
+// first k16 slice of a tile with an explicit C operand: rows lane/4 (c0, c1) and lane/4 + 8 (c2, c3) of the block
+__device__ __forceinline__ void mma_f16_init(float (&c)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1,
+                                             const float ca, const float cb)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%11,%11};"
+                 : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(ca), "f"(cb));
+}
+
+__device__ __forceinline__ float vmax4(const float (&c)[4])
+{
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(c[0]), "f"(c[1]), "f"(c[2]));
+    return fmaxf(d, c[3]);
+}
+
 // 0x3c00 (fp16 1.0) shifted left by s; PTX shl clamps shift amounts above 31, i.e. s >= 32 gives 0
 __device__ __forceinline__ uint32_t shl_one_f16(const uint32_t s)
 {
@@ -75,13 +91,64 @@ static __constant__ uint32_t c_emb16[17][2] = {
     {0x35553555u, 0x00003555u},  // V  (A, C, G)
 };
 
+// fp16 pair of the soft one-hot of base q of a row; kept out of line so that the hot loop stays small (instruction cache)
+static __device__ __noinline__ uint32_t soft_onehot_f16(const uint32_t* packed, const uint16_t* amask, const uint8_t* codes,
+                                                        const long long word_off, const int n_avail, const long long q, const int half)
+{
+    smg_row_t row;
+    row.word_off = word_off; row.n_avail = n_avail; row.g_off = 0; row.g_len = 0; row.n_own = 0;
+    return c_emb16[smg_fetch_code(packed, amask, codes, row, q)][half];
+}
+
 constexpr int kCandStage = 128;
+
+// Candidates of one 16-column block of one tile (rare path, out of line): ballot + prefix-popcount compaction into the
+// warp's stage, which is appended to the global candidate list with one atomic per flush.  Returns the new fill.
+static __device__ __noinline__ int emit_block(unsigned long long* s_cand, int nst, const float v0, const float v1, const float v2,
+                                              const float v3, const int s0, const int c1, const int* __restrict__ col_id,
+                                              const unsigned long long rowbits, const int pos_shift, unsigned long long* counter,
+                                              unsigned long long* __restrict__ cand, const unsigned long long cand_cap)
+{
+    const int lane = threadIdx.x;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int cidA = col_id[0], cidB = col_id[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float v = i == 0 ? v0 : i == 1 ? v1 : i == 2 ? v2 : v3;
+        const int s = s0 + (i & 1);
+        const bool is_cand = (v > 0.f) && (s < c1);
+        const unsigned m = __ballot_sync(SMG_FULL_MASK, is_cand);
+        if (m) {
+            if (is_cand)
+                s_cand[nst + __popc(m & lt_mask)] =
+                    rowbits | ((unsigned long long)(unsigned)s << pos_shift) | (unsigned long long)(unsigned)((i < 2) ? cidA : cidB);
+            nst += __popc(m);
+            __syncwarp();
+            if (nst > kCandStage - 32) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(counter, (unsigned long long)nst);
+                base = __shfl_sync(SMG_FULL_MASK, base, 0);
+                for (int j = lane; j < nst; j += 32)
+                    if (base + j < cand_cap) cand[base + j] = s_cand[j];
+                nst = 0;
+                __syncwarp();
+            }
+        }
+    }
+    return nst;
+}
 
 // KS = k16 steps (padded width = 4 * KS), NB = 16-column blocks per warp.  One warp per CTA; the warp walks its chunk
 // in tiles of 8 positions: B fragments for the next tile are generated (ALU) while the tensor pipe works on the
 // current one.
+// register caps on the occupancy steps of an SM sub-partition (see scan_regtab.cuh): 80/96/128/168 registers =
+// 6/5/4/3 one-warp CTAs
+template <int KS, int NB> struct HmmaMaxRegs {
+    static constexpr int v = NB > 4 ? 240 : KS == 1 ? 80 : KS == 2 ? 96 : KS == 3 ? 128 : 168;
+};
+
 template <int KS, int NB>
-__global__ void __launch_bounds__(32) scan_hmma_kernel(const HmmaParams hp)
+__global__ void __launch_bounds__(32) __maxnreg__((HmmaMaxRegs<KS, NB>::v)) scan_hmma_kernel(const HmmaParams hp)
 {
     const ScanParams& p = hp.sp;
     __shared__ unsigned long long s_cand[kCandStage];
@@ -131,28 +198,24 @@ __global__ void __launch_bounds__(32) scan_hmma_kernel(const HmmaParams hp)
         __syncwarp();
     };
 
-    // soft one-hot B fragments of the tile starting at pt (this lane: bases pt + n + 4*ks + kk (+2))
-    auto make_b = [&](const int pt, uint32_t (&b)[KS][2]) {
-        const int g = pt + n;
-        const int w0 = g >> 4, sh = 2 * (g & 15);
-        const unsigned long long lo = (unsigned long long)wp[w0] | ((unsigned long long)wp[w0 + 1] << 32);
-        const unsigned long long hi = (unsigned long long)wp[w0 + 2];
-        const unsigned long long win = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;  // 32 bases starting at g
-        // ambiguity mask of every base any lane of the warp touches in this tile: [pt, pt + 8 + 4*KS)
-        const int wt = pt >> 4;
-        const unsigned amb = (unsigned)ap[wt] | (unsigned)ap[wt + 1] | (unsigned)ap[wt + 2];
+    // Soft one-hot B fragments of the tile of 8 positions starting at pt (this lane: bases pt + n + 4*ks + kk (+2)).
+    // A tile starts at a multiple of 8 and n <= 7, so every lane of the warp reads the SAME three packed words
+    // w0..w2 (48 bases from the word that holds pt): they are loaded once per 16 positions at a warp-uniform address
+    // and the per-lane part is two funnel shifts by sft = 2 * (n + kk) (+16 for the second tile of the word).
+    const uint32_t bb16 = (uint32_t)bb << 4;  // 16 * bb
+    const int sft0 = 2 * (n + kk);
+    auto make_b = [&](const int pt, const uint32_t w0, const uint32_t w1, const uint32_t w2, const unsigned amb, const int sft,
+                      uint32_t (&b)[KS][2]) {
         if (amb == 0u) {
             // d = base ^ bb selects the half of the fp16 pair that is 1.0 (d = 0: low, 1: high, 2 and 3: neither):
-            // value = 0x3c00 << (16 * d) with the shift clamped, 16 * d taken straight from the window bits.
-            // Three instructions per fragment register (shift, and-xor, shift) after one per-lane pre-shift by kk.
-            const uint32_t lo32 = (uint32_t)win, hi32 = (uint32_t)(win >> 32);
-            const uint32_t klo = __funnelshift_r(lo32, hi32, 2 * kk), khi = hi32 >> (2 * kk);
-            const uint32_t bb16 = (uint32_t)bb << 4;  // 16 * bb
+            // value = 0x3c00 << (16 * d) with the shift clamped, 16 * d taken straight from the window bits:
+            // three instructions per fragment register (shift, and-xor, shift).
+            const uint32_t klo = __funnelshift_rc(w0, w1, sft), khi = __funnelshift_rc(w1, w2, sft);
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int bit = 2 * (4 * ks + 2 * h);  // bit offset of this row's base in the pre-shifted window
+                    const int bit = 2 * (4 * ks + 2 * h);  // bit offset of this row's base in the shifted window
                     uint32_t x;                            // 2-bit base code moved to bits 4..5 (fields never straddle)
                     if (bit == 0) x = klo << 4;
                     else if (bit < 32) x = klo >> (bit - 4);
@@ -161,22 +224,18 @@ __global__ void __launch_bounds__(32) scan_hmma_kernel(const HmmaParams hp)
                     b[ks][h] = shl_one_f16((x & 0x30u) ^ bb16);
                 }
             }
-        } else {  // IUPAC codes / 'Z' / padding somewhere near: soft one-hot from the code table
+        } else {  // IUPAC codes / 'Z' / padding somewhere near: soft one-hot from the code table (out of line, rare)
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int code = smg_fetch_code(p.packed, p.amask, p.codes, row, (long long)g + 4 * ks + kk + 2 * h);
-                    b[ks][h] = c_emb16[code][bb >> 1];
-                }
+                for (int h = 0; h < 2; ++h)
+                    b[ks][h] = soft_onehot_f16(p.packed, p.amask, p.codes, row.word_off, row.n_avail,
+                                               (long long)(pt + n) + 4 * ks + kk + 2 * h, bb >> 1);
             }
         }
     };
-
-    uint32_t b[KS][2];
-    make_b(c0, b);
-    for (int pt = c0; pt < c1; pt += 8) {
-        float c[NB][4];
+    // NB x KS tensor-core MMAs of one tile (the first slice accumulates onto RZ: no accumulator initialisation)
+    auto issue = [&](float (&c)[NB][4], const uint32_t (&b)[KS][2]) {
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
@@ -184,36 +243,47 @@ __global__ void __launch_bounds__(32) scan_hmma_kernel(const HmmaParams hp)
                 if (ks == 0) mma_f16_zero(c[blk], a[blk][ks], b[ks][0], b[ks][1]);
                 else mma_f16(c[blk], a[blk][ks], b[ks][0], b[ks][1]);
             }
-        make_b(pt + 8, b);  // next tile (ALU) while the tensor pipe drains this one; rows are padded: reading ahead is safe
-        // one vote for the whole tile (NB x 16 columns x 8 positions), then per block only when something passed
+    };
+    // one max-reduction + one vote for the whole tile (NB x 16 columns x 8 positions); per block and per accumulator
+    // only when something passed.  Candidates are rare: ballot + prefix-popcount compaction into the warp stage.
+    auto threshold = [&](const float (&c)[NB][4], const int pt) {
         bool any = false;
 #pragma unroll
         for (int blk = 0; blk < NB; ++blk)
             any = any || (fmaxf(c[blk][0], c[blk][1]) > tA[blk]) || (fmaxf(c[blk][2], c[blk][3]) > tB[blk]);
         if (__any_sync(SMG_FULL_MASK, any)) {
-#pragma unroll
+#pragma unroll 1
             for (int blk = 0; blk < NB; ++blk) {
-                const float mA = fmaxf(c[blk][0], c[blk][1]), mB = fmaxf(c[blk][2], c[blk][3]);
-                if (__any_sync(SMG_FULL_MASK, (mA > tA[blk]) | (mB > tB[blk]))) {
+                // (score - threshold) of this block's four accumulators; the block is selected at run time so that the
+                // rare path exists once (instruction cache), not once per block
+                float v0 = c[0][0] - tA[0], v1 = c[0][1] - tA[0], v2 = c[0][2] - tB[0], v3 = c[0][3] - tB[0];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int s = pt + q2 + (i & 1);
-                        const bool cand = (c[blk][i] > ((i < 2) ? tA[blk] : tB[blk])) && (s < c1);
-                        const unsigned m = __ballot_sync(SMG_FULL_MASK, cand);
-                        if (m) {
-                            if (cand) {
-                                const int cid = hp.col_id[colbase + blk * 16 + (lane >> 2) + ((i < 2) ? 0 : 8)];
-                                s_cand[nst + __popc(m & lt_mask)] =
-                                    rowbits | ((unsigned long long)(unsigned)s << (p.motif_bits + 1)) | (unsigned long long)(unsigned)cid;
-                            }
-                            nst += __popc(m);
-                            __syncwarp();
-                            if (nst > kCandStage - 32) flush();
-                        }
-                    }
-                }
+                for (int j = 1; j < NB; ++j)
+                    if (blk == j) { v0 = c[j][0] - tA[j]; v1 = c[j][1] - tA[j]; v2 = c[j][2] - tB[j]; v3 = c[j][3] - tB[j]; }
+                if (__any_sync(SMG_FULL_MASK, fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)) > 0.f))
+                    nst = emit_block(s_cand, nst, v0, v1, v2, v3, pt + q2, c1, hp.col_id + colbase + blk * 16 + (lane >> 2), rowbits,
+                                     p.motif_bits + 1, &p.counters[SMG_CTR_CANDIDATES], hp.cand, hp.cand_cap);
             }
         }
+    };
+
+    // c0 is a multiple of 16 (chunks are cut on word boundaries); two tiles per packed word
+    int wi = c0 >> 4;
+    uint32_t w0 = wp[wi], w1 = wp[wi + 1], w2 = wp[wi + 2];
+    unsigned a0 = ap[wi], a1 = ap[wi + 1], a2 = ap[wi + 2];
+    uint32_t b[KS][2];
+    float c[NB][4];
+    make_b(c0, w0, w1, w2, a0 | a1 | a2, sft0, b);
+    for (int pt = c0; pt < c1; pt += 16) {
+        issue(c, b);
+        make_b(pt + 8, w0, w1, w2, a0 | a1 | a2, sft0 + 16, b);  // next tile (ALU) while the tensor pipe drains this one
+        threshold(c, pt);
+        issue(c, b);
+        ++wi;  // rows are padded: reading one word ahead of the chunk is safe
+        w0 = w1; w1 = w2; w2 = wp[wi + 2];
+        a0 = a1; a1 = a2; a2 = ap[wi + 2];
+        make_b(pt + 16, w0, w1, w2, a0 | a1 | a2, sft0, b);
+        threshold(c, pt + 8);
     }
     if (nst > 0) flush();
 }
