@@ -247,23 +247,27 @@ __global__ void __launch_bounds__(32) __maxnreg__((HmmaMaxRegs<KS, NB>::v)) scan
     // one max-reduction + one vote for the whole tile (NB x 16 columns x 8 positions); per block and per accumulator
     // only when something passed.  Candidates are rare: ballot + prefix-popcount compaction into the warp stage.
     auto threshold = [&](const float (&c)[NB][4], const int pt) {
+        // first level: a predicate chain and one vote for the whole tile (NB x 16 columns x 8 positions)
         bool any = false;
 #pragma unroll
         for (int blk = 0; blk < NB; ++blk)
             any = any || (fmaxf(c[blk][0], c[blk][1]) > tA[blk]) || (fmaxf(c[blk][2], c[blk][3]) > tB[blk]);
-        if (__any_sync(SMG_FULL_MASK, any)) {
-#pragma unroll 1
-            for (int blk = 0; blk < NB; ++blk) {
-                // (score - threshold) of this block's four accumulators; the block is selected at run time so that the
-                // rare path exists once (instruction cache), not once per block
-                float v0 = c[0][0] - tA[0], v1 = c[0][1] - tA[0], v2 = c[0][2] - tB[0], v3 = c[0][3] - tB[0];
+        if (!__any_sync(SMG_FULL_MASK, any)) return;
+        // second level: bit blk of `hot` = some lane holds a candidate in block blk (one warp reduction)
+        unsigned mine = 0u;
 #pragma unroll
-                for (int j = 1; j < NB; ++j)
-                    if (blk == j) { v0 = c[j][0] - tA[j]; v1 = c[j][1] - tA[j]; v2 = c[j][2] - tB[j]; v3 = c[j][3] - tB[j]; }
-                if (__any_sync(SMG_FULL_MASK, fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)) > 0.f))
-                    nst = emit_block(s_cand, nst, v0, v1, v2, v3, pt + q2, c1, hp.col_id + colbase + blk * 16 + (lane >> 2), rowbits,
-                                     p.motif_bits + 1, &p.counters[SMG_CTR_CANDIDATES], hp.cand, hp.cand_cap);
-            }
+        for (int blk = 0; blk < NB; ++blk)
+            if ((fmaxf(c[blk][0], c[blk][1]) > tA[blk]) || (fmaxf(c[blk][2], c[blk][3]) > tB[blk])) mine |= 1u << blk;
+        unsigned hot = __reduce_or_sync(SMG_FULL_MASK, mine);
+        while (hot) {  // rare; the block is selected at run time so that the emission code exists once (instruction cache)
+            const int blk = __ffs((int)hot) - 1;
+            hot &= hot - 1u;
+            float v0 = c[0][0] - tA[0], v1 = c[0][1] - tA[0], v2 = c[0][2] - tB[0], v3 = c[0][3] - tB[0];
+#pragma unroll
+            for (int j = 1; j < NB; ++j)
+                if (blk == j) { v0 = c[j][0] - tA[j]; v1 = c[j][1] - tA[j]; v2 = c[j][2] - tB[j]; v3 = c[j][3] - tB[j]; }
+            nst = emit_block(s_cand, nst, v0, v1, v2, v3, pt + q2, c1, hp.col_id + colbase + blk * 16 + (lane >> 2), rowbits,
+                             p.motif_bits + 1, &p.counters[SMG_CTR_CANDIDATES], hp.cand, hp.cand_cap);
         }
     };
 
