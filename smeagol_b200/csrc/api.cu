@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -616,7 +617,17 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
         #ifndef SMG_HMMA_NB_SMALL
 #define SMG_HMMA_NB_SMALL 4
 #endif
-        auto nb_for = [](int ks) { return ks <= 3 ? SMG_HMMA_NB_SMALL : ks == 4 ? (SMG_HMMA_NB_SMALL == 8 ? 6 : 4) : ks <= 6 ? 4 : 3; };
+        // 16-column blocks per warp for each K depth; SMEAGOL_B200_HMMA_NB="n1,n2,...,n8" overrides (tuning only)
+        int nb_tab[9] = {0, SMG_HMMA_NB_SMALL, SMG_HMMA_NB_SMALL, SMG_HMMA_NB_SMALL, 4, 4, 4, 3, 3};
+        if (const char* e = getenv("SMEAGOL_B200_HMMA_NB")) {
+            int k = 1;
+            for (const char* q = e; *q && k <= 8; ++k) {
+                nb_tab[k] = atoi(q);
+                while (*q && *q != ',') ++q;
+                if (*q == ',') ++q;
+            }
+        }
+        auto nb_for = [&](int ks) { return nb_tab[ks]; };
         auto h16 = [](float v) { return (uint32_t)__half_as_ushort(__float2half_rn(v)); };
         for (int ks = 1; ks <= SMG_MAX_REGTAB_WIDTH / 4; ++ks) {
             std::vector<int> cols;  // motif * 2 + strand
