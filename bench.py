@@ -18,8 +18,10 @@ Timed regions
           memory, 2-bit pack kernel, scan, adjudicate, sort, D2H of the count table and counters.  The sorted site
           list stays on the device (config c2's result is the per-genome count table); wall clock around
           synchronised steps.
-  roofline : the dominant kernel (smg::scan_regtab_kernel, all bucket launches of one smg_scan call) timed live
-          with CUDA events; algorithmic work = 2*W lookup-adds per base x motif.
+  roofline : the dominant side of the scan timed live with CUDA events.  Hybrid engine (default): the tensor-core
+          prefilter + exact second pass (smg_scan_tc) -- bound "tensor", algorithmic FLOP = 2 strands x 2 x 4*W per
+          base x motif against the measured dense bf16 peak; the register-table side and the whole-scan lookup-add
+          rate against the measured FP32 add peak are reported beside it.  Engine regtab: bound "fp32_pipe".
   cpu_baseline / --impl reference : the reference pipeline's CPU port (oracle/ref_port.py) on a bounded sample.
 """
 import argparse
@@ -210,7 +212,15 @@ def main():
         plan.counts.zero_()
         if ev:
             ev[1].record()
-        plan.launch_scan()
+        if plan.engine == "auto":  # hybrid: time the two sides of the width split separately
+            plan.launch_regtab_side()
+            if ev:
+                ev[4].record()
+            plan.launch_tc_side()
+        else:
+            plan.launch_scan()
+            if ev:
+                ev[4].record()
         if ev:
             ev[2].record()
         if plan.engine == "regtab":
@@ -229,7 +239,7 @@ def main():
     if world > 1:
         dist.barrier()
     sampler.t_start = time.perf_counter()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     launches0 = _lib.launch_count()
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
@@ -242,6 +252,8 @@ def main():
     launches = _lib.launch_count() - launches0
     step_ms = np.array([e[0].elapsed_time(e[3]) for e in evs])
     scan_ms = np.array([e[1].elapsed_time(e[2]) for e in evs])
+    side_a_ms = np.array([e[1].elapsed_time(e[4]) for e in evs])  # register-table side (hybrid) / the whole scan
+    side_b_ms = np.array([e[4].elapsed_time(e[2]) for e in evs])  # tensor-core side (hybrid) / 0
     c = plan.counters.cpu().numpy()
     assert int(c[_lib.CTR_HITS_APPENDED]) == n_hits, "non-deterministic hit count"
     ms_per_step = float(step_ms.mean())
@@ -299,16 +311,46 @@ def main():
         except Exception:
             traffic = None
     algo_bytes = batch.total_words * 6 + n_hits * 12 + plan.counts.numel() * 4
-    roofline = {"bound": "fp32_pipe", "achieved": achieved_t, "peak": FP32_ADD_PEAK_T, "unit": "Tlookup-add/s",
-                "frac": achieved_t / FP32_ADD_PEAK_T, "traffic": traffic,
-                "kernel": "smg::scan_regtab_kernel (%d launches per step, one per width bucket)" % dset.n_buckets,
-                "kernel_ms": scan_s * 1e3, "kernel_share_of_step": scan_s * 1e3 / float(step_ms.mean()),
-                "peak_source": "FADD2 microbenchmark on this pool (profiles/microbench_fp32_r01.txt); nominal 148*128*1.965e9=37.2",
-                "lds_gather_roofline": {"peak": LDS_PEAK_T, "frac": achieved_t / LDS_PEAK_T,
-                                        "note": "BASELINE.md section 4 algorithmic bound of a shared-memory gather; the register-table kernel does no shared-memory lookups, so this fraction exceeds 1"},
-                "hbm": {"algorithmic_bytes": int(algo_bytes), "achieved_gbs": algo_bytes / scan_s / 1e9,
-                        "peak_gbs": peaks["hbm_gbs"], "frac": algo_bytes / scan_s / 1e9 / peaks["hbm_gbs"],
-                        "peaks": peaks_kind}}
+    widths64 = dset.widths.astype(np.int64)
+    fp32_view = {"achieved": achieved_t, "peak": FP32_ADD_PEAK_T, "unit": "Tlookup-add/s", "frac": achieved_t / FP32_ADD_PEAK_T,
+                 "scan_ms": scan_s * 1e3,
+                 "note": "whole scan (both engines): 2*W lookup-adds per base x motif (SURVEY 8d) over the event-timed scan, against "
+                         "the measured FP32 add peak that bounds the register-table kernel (profiles/microbench_fp32_r01.txt)",
+                 "lds_gather_roofline": {"peak": LDS_PEAK_T, "frac": achieved_t / LDS_PEAK_T,
+                                         "note": "BASELINE.md section 4 bound of a shared-memory gather; neither engine does "
+                                                 "shared-memory lookups, so this fraction exceeds 1"}}
+    hbm_view = {"algorithmic_bytes": int(algo_bytes), "achieved_gbs": algo_bytes / scan_s / 1e9, "peak_gbs": peaks["hbm_gbs"],
+                "frac": algo_bytes / scan_s / 1e9 / peaks["hbm_gbs"], "peaks": peaks_kind}
+    if plan.engine == "auto" and float(side_b_ms.mean()) > float(side_a_ms.mean()):
+        # dominant kernel: the tensor-core prefilter (scan_hmma_kernel, one launch per K depth, concurrent)
+        tc = widths64 >= dset.tc_min_width
+        tc_s = float(side_b_ms.mean()) * 1e-3
+        flops = total_bases * 2 * int((2 * 4 * widths64[tc]).sum())            # 2 strands x 2 flop x 4W per base x motif
+        flops_padded = total_bases * 2 * int((2 * 16 * ((widths64[tc] + 3) // 4)).sum())  # K padded to 16-row slices
+        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+        roofline = {"bound": "tensor", "achieved": flops / tc_s / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": flops / tc_s / 1e12 / peak_tf, "traffic": traffic,
+                    "kernel": "smg::scan_hmma_kernel + finalize_candidates_kernel (smg_scan_tc: %d PWMs of width >= %d)" % (
+                        int(tc.sum()), dset.tc_min_width),
+                    "kernel_ms": tc_s * 1e3, "kernel_share_of_step": tc_s * 1e3 / float(step_ms.mean()),
+                    "algorithmic": "2 strands x 2 flop x 4*W per base x motif (one-hot contraction, SURVEY 8d); padded to "
+                                   "16-row K slices the kernel executes %.1f TFLOP/s" % (flops_padded / tc_s / 1e12),
+                    "peak_source": "MEASURED_PEAKS.json dense bf16 (%s, %s); the kernel issues warp-level mma.sync (fp16), whose "
+                                   "own measured ceiling on this pool is 553 TFLOP/s (DESIGN 4.4): frac of that = %.3f" % (
+                                       "sustained" if "bf16_tflops_sustained" in peaks else "burst", peaks_kind,
+                                       flops_padded / tc_s / 1e12 / 553.0),
+                    "other_side": {"kernel": "smg::scan_regtab_kernel + adjudicate_kernel (smg_scan: %d PWMs narrower than %d)" % (
+                        int((~tc).sum()), dset.tc_min_width), "kernel_ms": float(side_a_ms.mean()),
+                        "Tlookup_add_per_s": total_bases * 2 * int(widths64[~tc].sum()) / (float(side_a_ms.mean()) * 1e-3) / 1e12,
+                        "frac_of_fp32_add_peak": total_bases * 2 * int(widths64[~tc].sum()) / (float(side_a_ms.mean()) * 1e-3) / 1e12 / FP32_ADD_PEAK_T},
+                    "fp32_pipe": fp32_view, "hbm": hbm_view}
+    else:
+        roofline = {"bound": "fp32_pipe", "achieved": achieved_t, "peak": FP32_ADD_PEAK_T, "unit": "Tlookup-add/s",
+                    "frac": achieved_t / FP32_ADD_PEAK_T, "traffic": traffic,
+                    "kernel": "smg::scan_regtab_kernel (%d launches per step, one per width bucket)" % dset.n_buckets,
+                    "kernel_ms": scan_s * 1e3, "kernel_share_of_step": scan_s * 1e3 / float(step_ms.mean()),
+                    "peak_source": "FADD2 microbenchmark on this pool (profiles/microbench_fp32_r01.txt); nominal 148*128*1.965e9=37.2",
+                    "lds_gather_roofline": fp32_view["lds_gather_roofline"], "hbm": hbm_view}
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         v, det = cpu_reference_run(pw, genomes, args.cpu_sample)

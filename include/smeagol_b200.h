@@ -77,7 +77,7 @@ uint64_t smg_launch_count(void);
  * concatenated row-major (sum(widths) x 4, columns A,C,G,T), HOST memory.  Builds the device tables: natural
  * layout, reverse-complement tables, and the lane-major register-table groups of the fused scan kernel. */
 int smg_pwmset_create(const float* h_weights, const int32_t* h_widths, int32_t n_motifs, smg_pwmset_t* out);
-/* Hybrid engine: PWMs narrower than tc_min_width (0 = no split, else 4*j+1) are scanned by smg_scan (register-table
+/* Hybrid engine: PWMs narrower than tc_min_width (0 = no split, else a width in 1..33) are scanned by smg_scan (register-table
  * kernel), the others by smg_scan_tc (tensor-core prefilter + exact second pass); a complete scan calls both on the
  * same hit / count / counter buffers.  With tc_min_width = 0 either entry point alone covers every PWM. */
 int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int32_t n_motifs, int32_t tc_min_width,

@@ -517,8 +517,8 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
                             smg_pwmset_t* out)
 {
     if (!h_weights || !h_widths || n_motifs <= 0 || !out) return fail(SMG_ERR_INVALID, "smg_pwmset_create: bad argument");
-    if (tc_min_width != 0 && (tc_min_width < 1 || (tc_min_width - 1) % 4 != 0))
-        return fail(SMG_ERR_INVALID, "smg_pwmset_create_split: tc_min_width must be 0 or 4*j + 1");
+    if (tc_min_width < 0 || tc_min_width > SMG_MAX_REGTAB_WIDTH + 1)
+        return fail(SMG_ERR_INVALID, "smg_pwmset_create_split: tc_min_width must be 0 (no split) or a width in 1..33");
     int rc = init_lut();
     if (rc != SMG_OK) return rc;
     smg_pwmset* s = new smg_pwmset();
@@ -632,7 +632,10 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
         for (int ks = 1; ks <= SMG_MAX_REGTAB_WIDTH / 4; ++ks) {
             std::vector<int> cols;  // motif * 2 + strand
             for (int m = 0; m < n_motifs; ++m)
-                if ((h_widths[m] + 3) / 4 == ks) { cols.push_back(m * 2); cols.push_back(m * 2 + 1); }
+                if ((h_widths[m] + 3) / 4 == ks && (s->split == 0 || h_widths[m] >= s->split)) {  // tensor-core side only
+                    cols.push_back(m * 2);
+                    cols.push_back(m * 2 + 1);
+                }
             if (cols.empty()) continue;
             const int nb = nb_for(ks), per = nb * 16;
             const int ncg = (int)((cols.size() + per - 1) / per);
@@ -801,8 +804,7 @@ int smg_scan_tc(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amas
     if ((d_hit_keys == nullptr) != (d_hit_scores == nullptr)) return fail(SMG_ERR_INVALID, "smg_scan_tc: hit buffers must both be set or NULL");
     if (n_chunks == 0) return SMG_OK;
     {   // nothing on the tensor-core side of the split (e.g. no PWM that wide in the set): no launches at all
-        bool any = false;
-        for (const smg_pwmset::HmmaBucket& b : s->hbuckets) any = any || !(s->split > 0 && 4 * b.ks < s->split);
+        const bool any = !s->hbuckets.empty();  // with a split the fragment tables hold the tensor-core side only
         if (!any && (s->wide.empty() || s->split > 0)) return SMG_OK;
     }
     cudaStream_t st = (cudaStream_t)stream;
@@ -825,7 +827,6 @@ int smg_scan_tc(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amas
     SMG_CUDA(cudaEventRecord(pool->fork, st));
     int bi = 0;
     for (const smg_pwmset::HmmaBucket& b : s->hbuckets) {
-        if (s->split > 0 && 4 * b.ks < s->split) continue;  // the register-table engine owns these (smg_scan)
         smg_hmma_launch_fn fn = smg_get_hmma_launcher(b.ks, b.nb);
         if (!fn) return fail(SMG_ERR_INVALID, "smg_scan_tc: no kernel for KS " + std::to_string(b.ks));
         cudaStream_t bs = (bi == 0) ? st : pool->side[(bi - 1) % StreamPool::kSide];

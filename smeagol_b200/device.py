@@ -19,7 +19,7 @@ ROW_PAD_BASES = 96  # every row is followed by at least this many 'Z' bases (hal
 NEAR_REL = 1e-5     # half-width of the near-threshold band, relative to sum_k max_b |T[k,b]|
 STRANDS = {"none": 1, "only": 2, "both": 3}
 DEFAULT_ENGINE = "regtab"
-DEFAULT_TC_MIN_WIDTH = 9  # measured: c2 1028 vs 960, c3 1206 vs 1127, c4 1259 vs 1184 Gbase*motif/s against a split at 13 (tools/sweep_split.sh)
+DEFAULT_TC_MIN_WIDTH = 10  # measured (tools/sweep_split.sh): c2 1144, c3 1381, c4 1419 Gbase*motif/s; split 9: 1137 / 1336 / 1428; split 13: 960 / 1127 / 1184
 
 
 def _require_cuda(device=None):
@@ -145,7 +145,7 @@ class DevicePWMSet:
     reverse-complement tables and lane-major register-table groups, built by smg_pwmset_create)."""
 
     def __init__(self, weights, device=None, tc_min_width=None):
-        """tc_min_width: PWMs at least this wide (4*j+1) go to the tensor-core engine, narrower ones to the
+        """tc_min_width: PWMs at least this wide go to the tensor-core engine, narrower ones to the
         register-table engine (engine 'auto'); 0 = no split (either engine alone covers every PWM)."""
         self.device = _require_cuda(device)
         if tc_min_width is None:
@@ -333,20 +333,30 @@ class ScanPlan:
 
     def launch_scan(self):
         """Enqueue the scan kernels only (the tensor-core engine's exact second pass includes the adjudication)."""
-        b, lib = self.batch, self.lib
         if self.engine == "auto":  # register-table side (+ its adjudication), then the tensor-core side
             self._launch_regtab()
             if self.adjudicate:
                 self.launch_adjudicate()
         if self.engine in ("hmma", "auto"):
-            _lib.check(lib.smg_scan_tc(self.pwmset.handle, _ptr(b.packed), _ptr(b.amask), _ptr(b.codes), _ptr(b.d_rows), b.n_rows,
-                                       _ptr(self.d_out_rows), _ptr(self.d_chunks), self.n_chunks, self.chunk_len, self.strands,
-                                       _ptr(self.d_lo), _ptr(self.d_hi), _ptr(self.d_pre), _ptr(self.d_thr), self.pos_bits,
-                                       self.motif_bits, self.cand_pos_bits, _ptr(self.cand), self.cand_cap, _ptr(self.keys),
-                                       _ptr(self.scores), self.hit_cap, _ptr(self.counts), _ptr(self.counters), _stream()),
-                       "smg_scan_tc")
+            self.launch_tc_side()
             return
         self._launch_regtab()
+
+    def launch_regtab_side(self):
+        """Register-table engine on its side of the width split, with its fp64 adjudication (engine 'auto')."""
+        self._launch_regtab()
+        if self.adjudicate:
+            self.launch_adjudicate()
+
+    def launch_tc_side(self):
+        """Tensor-core prefilter + exact second pass on its side of the width split."""
+        b, lib = self.batch, self.lib
+        _lib.check(lib.smg_scan_tc(self.pwmset.handle, _ptr(b.packed), _ptr(b.amask), _ptr(b.codes), _ptr(b.d_rows), b.n_rows,
+                                   _ptr(self.d_out_rows), _ptr(self.d_chunks), self.n_chunks, self.chunk_len, self.strands,
+                                   _ptr(self.d_lo), _ptr(self.d_hi), _ptr(self.d_pre), _ptr(self.d_thr), self.pos_bits,
+                                   self.motif_bits, self.cand_pos_bits, _ptr(self.cand), self.cand_cap, _ptr(self.keys),
+                                   _ptr(self.scores), self.hit_cap, _ptr(self.counts), _ptr(self.counters), _stream()),
+                   "smg_scan_tc")
 
     def _launch_regtab(self):
         b, lib = self.batch, self.lib

@@ -477,7 +477,7 @@ def test_hybrid_engine_split_bit_identical():
     amb = "ACGTNWSMKRYBDHVZ"
     pa = np.array([0.23] * 4 + [0.08 / 12] * 12)
     seqs = [rand_seq(rng, 1500), rand_seq(rng, 777, amb, pa / pa.sum()), rand_seq(rng, 31), ""]
-    for split in (5, 13, 21):
+    for split in (5, 10, 13, 22, 33):  # any width may be the split, also inside a K-depth class and above every PWM
         model = sb.models.PWMModel(df, tc_min_width=split)
         res, exp = check_against_oracle(model, seqs, 0.55, "both", chunk_len=256)
         assert res.stats["engine"] == "auto"
