@@ -75,7 +75,9 @@ uint64_t smg_launch_count(void);
 
 /* PWMModel.__init__ / _pad_weights / set_model_weights (models.py:35-48, 70-90): weights are the fp32-cast PWMs
  * concatenated row-major (sum(widths) x 4, columns A,C,G,T), HOST memory.  Builds the device tables: natural
- * layout, reverse-complement tables, and the lane-major register-table groups of the fused scan kernel. */
+ * layout, reverse-complement tables, and the lane-major register-table groups of the fused scan kernel.
+ * Non-finite weights are stored as given; to reproduce the reference (0 * -inf = NaN in its one-hot contraction, so
+ * such a PWM never yields a site) pass +inf thresholds for those PWMs to the scan calls. */
 int smg_pwmset_create(const float* h_weights, const int32_t* h_widths, int32_t n_motifs, smg_pwmset_t* out);
 /* Hybrid engine: PWMs narrower than tc_min_width (0 = no split, else a width in 1..33) are scanned by smg_scan (register-table
  * kernel), the others by smg_scan_tc (tensor-core prefilter + exact second pass); a complete scan calls both on the

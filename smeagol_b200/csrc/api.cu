@@ -533,8 +533,9 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
         tot += h_widths[m];
         s->max_w = std::max(s->max_w, (int)h_widths[m]);
     }
-    for (int64_t i = 0; i < tot * 4; ++i)
-        if (!std::isfinite(h_weights[i])) { delete s; return fail(SMG_ERR_INVALID, "smg_pwmset_create: non-finite PWM weight"); }
+    // Non-finite weights (log2 of a zero probability) are stored as given.  The reference's one-hot contraction turns
+    // every window of such a PWM into NaN (never a hit); the kernels add the selected weight only, so the caller
+    // reproduces that by passing +inf thresholds for these PWMs (smeagol_b200/device.py does).
 
     // ---- lane groups: PWMs sorted by width; a lane holds NM = 2 PWMs while 2 * width <= 2 * kPairMaxWidth (more adds
     // per uniform branch), else 1; 32 * NM PWMs per group; remainders are carried up to the next width (zero padding)

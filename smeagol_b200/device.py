@@ -145,7 +145,8 @@ class DevicePWMSet:
     reverse-complement tables and lane-major register-table groups, built by smg_pwmset_create)."""
 
     def __init__(self, weights, device=None, tc_min_width=None):
-        """tc_min_width: PWMs at least this wide go to the tensor-core engine, narrower ones to the
+        """Non-finite weights (log2 of a zero probability) are accepted as in the reference, where such a PWM never yields
+        a site (ScanPlan switches it off).  tc_min_width: PWMs at least this wide go to the tensor-core engine, narrower ones to the
         register-table engine (engine 'auto'); 0 = no split (either engine alone covers every PWM)."""
         self.device = _require_cuda(device)
         if tc_min_width is None:
@@ -156,8 +157,6 @@ class DevicePWMSet:
         for w in w32:
             if w.ndim != 2 or w.shape[1] != 4:
                 raise ValueError("PWM weights must have shape (W, 4)")
-            if not np.all(np.isfinite(w)):
-                raise ValueError("PWM weights must be finite (the reference's conv yields NaN for -inf entries)")
         self.n_motifs = len(w32)
         self.widths = np.array([w.shape[0] for w in w32], dtype=np.int32)
         flat = np.concatenate([w.reshape(-1) for w in w32]).astype(np.float32)
@@ -278,7 +277,13 @@ class ScanPlan:
         M = pwmset.n_motifs
         thr64 = np.ascontiguousarray(thr64, dtype=np.float64)
         assert thr64.shape == (M,)
-        lo, hi = threshold_bounds(thr64, pwmset.abs_scale, adjudicate)
+        # A PWM with a non-finite weight (log2 of a zero probability) never scores a hit in the reference: its one-hot
+        # contraction multiplies every weight of a row, 0 * -inf = NaN, and NaN > thr is False (models.py:52-68, :108).
+        # The kernels add only the selected weight, so such PWMs are switched off through their thresholds.
+        dead = ~np.isfinite(np.asarray(pwmset.abs_scale, dtype=np.float64)) | ~np.isfinite(thr64)
+        scale = np.where(dead, 0.0, np.asarray(pwmset.abs_scale, dtype=np.float64))
+        thr64 = np.where(dead, np.inf, thr64)
+        lo, hi = threshold_bounds(thr64, scale, adjudicate)
         self.motif_bits = _bits(M)
         self.pos_bits = _bits(batch.max_g_len + 1)
         self.row_bits = _bits(n_out_rows)
@@ -304,7 +309,7 @@ class ScanPlan:
         self.cand_cap = 0
         if self.engine in ("hmma", "auto"):
             # prefilter bound: below thr_lo by 2^-9 * sum_k max_b |T| (>= 4x the fp16 rounding error of the operands)
-            pre = _round_down_f32(lo.astype(np.float64) - 2.0 ** -9 * np.asarray(pwmset.abs_scale, dtype=np.float64) - 1e-30)
+            pre = _round_down_f32(lo.astype(np.float64) - 2.0 ** -9 * scale - 1e-30)
             self.d_pre = torch.from_numpy(pre).to(dev)
             self.cand_pos_bits = _bits(int(batch.rows_host["n_avail"].max()) + 2)
             if self.cand_pos_bits + self.motif_bits + 1 + _bits(batch.n_rows) > 62:

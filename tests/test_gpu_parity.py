@@ -487,3 +487,26 @@ def test_hybrid_engine_split_bit_identical():
     plain = sb.models.PWMModel(df, tc_min_width=0)
     res, _ = check_against_oracle(plain, seqs, 0.55, "both")
     assert res.stats["engine"] == "regtab"
+
+
+@pytest.mark.gpu
+def test_nonfinite_weights_never_hit_like_the_reference():
+    """log2 of a zero probability gives -inf weights.  The reference contracts the full one-hot vector with every
+    weight of a row (models.py:52-68): 0 * -inf = NaN, NaN > thr is False (models.py:108), so such a PWM has no site
+    anywhere.  Both engines must agree (they add only the selected weight and would otherwise report hits)."""
+    sb = _sb()
+    rng = np.random.default_rng(47)
+    ws = []
+    for i, W in enumerate([6, 8, 9, 11, 12, 14, 17, 24]):
+        w = np.log2((rng.dirichlet([0.5] * 4, size=W) + 0.01) / 1.04 / 0.25)
+        if i % 2 == 1:
+            w[rng.integers(0, W), rng.integers(0, 4)] = -np.inf
+        ws.append(w)
+    df = pd.DataFrame({"Matrix_id": ["M%d" % i for i in range(len(ws))], "weights": ws})
+    seqs = [rand_seq(rng, 3000), rand_seq(rng, 500, "ACGTN", [0.24, 0.24, 0.24, 0.24, 0.04])]
+    with np.errstate(invalid="ignore"):
+        for split in (0, 5, 10):
+            model = sb.models.PWMModel(df, tc_min_width=split)
+            res, exp = check_against_oracle(model, seqs, 0.5, "both")
+            assert set(np.unique(exp["motif"])) == {0, 2, 4, 6}
+            assert res.stats["n_near"] < 1000  # the dead PWMs are switched off, not sent to the adjudicator
