@@ -19,7 +19,12 @@ for r in csv.reader(io.StringIO(raw)):
     elif cur is not None:
         cur["rows"].append(r)
 out = []
+seen = set()
 for b in blocks:
+    sig = (b["name"], len(b["rows"]), tuple(b["rows"][1][:6]) if len(b["rows"]) > 1 else ())
+    if sig in seen:  # the source page lists a launch once per view
+        continue
+    seen.add(sig)
     hdr = b["rows"][0]
     data = [r for r in b["rows"][1:] if len(r) == len(hdr)]
     isrc, ie, isamp = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
