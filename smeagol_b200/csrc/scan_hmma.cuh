@@ -102,34 +102,42 @@ static __device__ __noinline__ uint32_t soft_onehot_f16(const uint32_t* packed, 
 
 constexpr int kCandStage = 128;
 
-// Candidates of one 16-column block of one tile (rare path, out of line): ballot + prefix-popcount compaction into the
-// warp's stage, which is appended to the global candidate list with one atomic per flush.  Returns the new fill.
-static __device__ __noinline__ int emit_block(unsigned long long* s_cand, int nst, const float v0, const float v1, const float v2,
-                                              const float v3, const int s0, const int c1, const int* __restrict__ col_id,
-                                              const unsigned long long rowbits, const int pos_shift, unsigned long long* counter,
-                                              unsigned long long* __restrict__ cand, const unsigned long long cand_cap)
+constexpr int kTcQueue = 32;  // per-lane candidate queue slots (a tile adds at most 4 * NB <= 16 per lane)
+
+// Drain of the per-lane candidate queues (out of line, runs a few times per chunk): every lane decodes its tags
+// (tile << 5 | block << 2 | accumulator) into (window start, column), the warp compacts them with ballot +
+// prefix-popcount into its stage, and the stage is appended to the global candidate list with one atomic per flush.
+// Returns the new stage fill.
+static __device__ __noinline__ int drain_queues(const uint32_t* s_q, const int qn, unsigned long long* s_cand, int nst, const int c0,
+                                                const int c1, const int* __restrict__ col_id, const unsigned long long rowbits,
+                                                const int pos_shift, unsigned long long* counter,
+                                                unsigned long long* __restrict__ cand, const unsigned long long cand_cap)
 {
     const int lane = threadIdx.x;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int cidA = col_id[0], cidB = col_id[8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float v = i == 0 ? v0 : i == 1 ? v1 : i == 2 ? v2 : v3;
-        const int s = s0 + (i & 1);
-        const bool is_cand = (v > 0.f) && (s < c1);
+    const int q2 = (lane & 3) * 2;
+    const int maxn = __reduce_max_sync(SMG_FULL_MASK, qn);
+    for (int j = 0; j < maxn; ++j) {
+        const bool have = j < qn;
+        const unsigned tag = have ? s_q[j * 32 + lane] : 0u;
+        const int i = (int)(tag & 3u), blk = (int)((tag >> 2) & 7u);
+        const int s = c0 + (int)(tag >> 5) * 8 + q2 + (i & 1);
+        const bool is_cand = have && (s < c1);
         const unsigned m = __ballot_sync(SMG_FULL_MASK, is_cand);
         if (m) {
-            if (is_cand)
+            if (is_cand) {
+                const int cid = col_id[blk * 16 + (lane >> 2) + ((i < 2) ? 0 : 8)];
                 s_cand[nst + __popc(m & lt_mask)] =
-                    rowbits | ((unsigned long long)(unsigned)s << pos_shift) | (unsigned long long)(unsigned)((i < 2) ? cidA : cidB);
+                    rowbits | ((unsigned long long)(unsigned)s << pos_shift) | (unsigned long long)(unsigned)cid;
+            }
             nst += __popc(m);
             __syncwarp();
             if (nst > kCandStage - 32) {
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(counter, (unsigned long long)nst);
                 base = __shfl_sync(SMG_FULL_MASK, base, 0);
-                for (int j = lane; j < nst; j += 32)
-                    if (base + j < cand_cap) cand[base + j] = s_cand[j];
+                for (int k = lane; k < nst; k += 32)
+                    if (base + k < cand_cap) cand[base + k] = s_cand[k];
                 nst = 0;
                 __syncwarp();
             }
@@ -152,6 +160,8 @@ __global__ void __launch_bounds__(32) __maxnreg__((HmmaMaxRegs<KS, NB>::v)) scan
 {
     const ScanParams& p = hp.sp;
     __shared__ unsigned long long s_cand[kCandStage];
+    __shared__ uint32_t s_q[kTcQueue * 32];  // per-lane candidate queues, [slot][lane]
+    static_assert(4 * NB <= kTcQueue / 2, "a tile must fit in half a queue");
     const int lane = threadIdx.x;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int colgroup = hp.first_colgroup + blockIdx.y;
@@ -246,6 +256,17 @@ __global__ void __launch_bounds__(32) __maxnreg__((HmmaMaxRegs<KS, NB>::v)) scan
     };
     // one max-reduction + one vote for the whole tile (NB x 16 columns x 8 positions); per block and per accumulator
     // only when something passed.  Candidates are rare: ballot + prefix-popcount compaction into the warp stage.
+    // Candidate handling in two levels (as in scan_regtab.cuh): a lane whose accumulator exceeds the prefilter threshold
+    // appends a 32-bit tag to ITS OWN queue in shared memory (predicated store + pointer bump: no ballot, shuffle or
+    // call in the scan loop); the queues are drained together when one may overflow and at the end of the chunk.
+    const unsigned qbase = (unsigned)__cvta_generic_to_shared(&s_q[lane]);
+    unsigned qaddr = qbase;
+    auto drain = [&]() {
+        nst = drain_queues(s_q, (int)((qaddr - qbase) >> 7), s_cand, nst, c0, c1, hp.col_id + colbase, rowbits, p.motif_bits + 1,
+                           &p.counters[SMG_CTR_CANDIDATES], hp.cand, hp.cand_cap);
+        qaddr = qbase;
+        __syncwarp();
+    };
     auto threshold = [&](const float (&c)[NB][4], const int pt) {
         // first level: a predicate chain and one vote for the whole tile (NB x 16 columns x 8 positions)
         bool any = false;
@@ -253,22 +274,18 @@ __global__ void __launch_bounds__(32) __maxnreg__((HmmaMaxRegs<KS, NB>::v)) scan
         for (int blk = 0; blk < NB; ++blk)
             any = any || (fmaxf(c[blk][0], c[blk][1]) > tA[blk]) || (fmaxf(c[blk][2], c[blk][3]) > tB[blk]);
         if (!__any_sync(SMG_FULL_MASK, any)) return;
-        // second level: bit blk of `hot` = some lane holds a candidate in block blk (one warp reduction)
-        unsigned mine = 0u;
+        const unsigned tagbase = (unsigned)((pt - c0) >> 3) << 5;
 #pragma unroll
-        for (int blk = 0; blk < NB; ++blk)
-            if ((fmaxf(c[blk][0], c[blk][1]) > tA[blk]) || (fmaxf(c[blk][2], c[blk][3]) > tB[blk])) mine |= 1u << blk;
-        unsigned hot = __reduce_or_sync(SMG_FULL_MASK, mine);
-        while (hot) {  // rare; the block is selected at run time so that the emission code exists once (instruction cache)
-            const int blk = __ffs((int)hot) - 1;
-            hot &= hot - 1u;
-            float v0 = c[0][0] - tA[0], v1 = c[0][1] - tA[0], v2 = c[0][2] - tB[0], v3 = c[0][3] - tB[0];
+        for (int blk = 0; blk < NB; ++blk) {
 #pragma unroll
-            for (int j = 1; j < NB; ++j)
-                if (blk == j) { v0 = c[j][0] - tA[j]; v1 = c[j][1] - tA[j]; v2 = c[j][2] - tB[j]; v3 = c[j][3] - tB[j]; }
-            nst = emit_block(s_cand, nst, v0, v1, v2, v3, pt + q2, c1, hp.col_id + colbase + blk * 16 + (lane >> 2), rowbits,
-                             p.motif_bits + 1, &p.counters[SMG_CTR_CANDIDATES], hp.cand, hp.cand_cap);
+            for (int i = 0; i < 4; ++i) {
+                if (c[blk][i] > ((i < 2) ? tA[blk] : tB[blk])) {
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(qaddr), "r"(tagbase + (unsigned)(blk * 4 + i)) : "memory");
+                    qaddr += 128u;
+                }
+            }
         }
+        if (__any_sync(SMG_FULL_MASK, qaddr > qbase + (unsigned)(kTcQueue - 4 * NB) * 128u)) drain();
     };
 
     // c0 is a multiple of 16 (chunks are cut on word boundaries); two tiles per packed word
@@ -289,6 +306,7 @@ __global__ void __launch_bounds__(32) __maxnreg__((HmmaMaxRegs<KS, NB>::v)) scan
         make_b(pt + 16, w0, w1, w2, a0 | a1 | a2, sft0, b);
         threshold(c, pt + 8);
     }
+    drain();
     if (nst > 0) flush();
 }
 
