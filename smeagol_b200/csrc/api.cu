@@ -615,11 +615,8 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
     std::vector<int64_t> cg_off;
     std::vector<int32_t> col_id;
     {
-        #ifndef SMG_HMMA_NB_SMALL
-#define SMG_HMMA_NB_SMALL 4
-#endif
         // 16-column blocks per warp for each K depth; SMEAGOL_B200_HMMA_NB="n1,n2,...,n8" overrides (tuning only)
-        int nb_tab[9] = {0, SMG_HMMA_NB_SMALL, SMG_HMMA_NB_SMALL, SMG_HMMA_NB_SMALL, 4, 4, 4, 3, 3};
+        int nb_tab[9] = {0, 4, 3, 4, 4, 4, 4, 3, 3};  // measured (tools/sweep_nb.sh); K = 32 is hit-dense: smaller tiles, 6 warps
         if (const char* e = getenv("SMEAGOL_B200_HMMA_NB")) {
             int k = 1;
             for (const char* q = e; *q && k <= 8; ++k) {
@@ -642,8 +639,9 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
             const int ncg = (int)((cols.size() + per - 1) / per);
             // column groups of different buckets have different sizes: col arrays are indexed by colgroup * per within
             // the bucket, so every bucket gets its own base such that (first_colgroup * per) is its first column
-            while ((int64_t)col_id.size() % per) col_id.push_back(-1);
-            const int first_cg = (int)(col_id.size() / per);
+            // (and beyond every column-group index already used by a bucket with a different group size)
+            const int first_cg = std::max((int)((col_id.size() + per - 1) / per), (int)cg_off.size());
+            col_id.resize((size_t)first_cg * per, -1);
             s->hbuckets.push_back({ks, nb, first_cg, ncg});
             for (int cg = 0; cg < ncg; ++cg) {
                 while ((int64_t)cg_off.size() < first_cg + cg) cg_off.push_back(0);

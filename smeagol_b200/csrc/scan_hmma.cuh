@@ -152,7 +152,10 @@ static __device__ __noinline__ int drain_queues(const uint32_t* s_q, const int q
 // register caps on the occupancy steps of an SM sub-partition (see scan_regtab.cuh): 80/96/128/168 registers =
 // 6/5/4/3 one-warp CTAs
 template <int KS, int NB> struct HmmaMaxRegs {
-    static constexpr int v = NB > 4 ? 240 : KS == 1 ? 80 : KS == 2 ? 96 : KS == 3 ? 128 : 168;
+    static constexpr int v = NB > 6 ? 240 : NB > 4 ? (KS <= 2 ? 128 : 168)
+                             : NB == 4 ? (KS == 1 ? 80 : KS == 2 ? 96 : KS == 3 ? 128 : 168)
+                             : NB == 3 ? (KS == 1 ? 64 : KS == 2 ? 80 : KS == 3 ? 96 : KS <= 5 ? 128 : 168)
+                                       : (KS == 1 ? 64 : KS == 2 ? 72 : KS == 3 ? 80 : 128);
 };
 
 template <int KS, int NB>
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(32) __maxnreg__((HmmaMaxRegs<KS, NB>::v)) scan
     const ScanParams& p = hp.sp;
     __shared__ unsigned long long s_cand[kCandStage];
     __shared__ uint32_t s_q[kTcQueue * 32];  // per-lane candidate queues, [slot][lane]
-    static_assert(4 * NB <= kTcQueue / 2, "a tile must fit in half a queue");
+    static_assert(4 * NB <= kTcQueue - 8, "a tile must fit in the queue");
     const int lane = threadIdx.x;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int colgroup = hp.first_colgroup + blockIdx.y;

@@ -19,7 +19,7 @@ ROW_PAD_BASES = 96  # every row is followed by at least this many 'Z' bases (hal
 NEAR_REL = 1e-5     # half-width of the near-threshold band, relative to sum_k max_b |T[k,b]|
 STRANDS = {"none": 1, "only": 2, "both": 3}
 DEFAULT_ENGINE = "regtab"
-DEFAULT_TC_MIN_WIDTH = 10  # measured (tools/sweep_split.sh): c2 1144, c3 1381, c4 1419 Gbase*motif/s; split 9: 1137 / 1336 / 1428; split 13: 960 / 1127 / 1184
+DEFAULT_TC_MIN_WIDTH = 7  # measured per width (profiles/r01_bench_widths.txt): the register-table engine wins up to W = 6 (hit density >= 6e-3 at thr 0.7), the tensor-core prefilter from W = 7
 
 
 def _require_cuda(device=None):
