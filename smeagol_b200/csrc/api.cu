@@ -400,9 +400,12 @@ __global__ void hmma_thr_kernel(const int32_t* __restrict__ col_id, const float*
 }
 
 // Exact second pass of the tensor-core path: every candidate (row, start, motif, strand) emitted by the fp16 prefilter is
+#ifndef SMG_FINALIZE_MIN_BLOCKS
+#define SMG_FINALIZE_MIN_BLOCKS 4
+#endif
 // re-scored in fp32 in the register-table kernel's summation order, the near-threshold band is adjudicated in fp64,
 // and hits / counts are produced exactly as smg_scan + smg_adjudicate would.
-__global__ void __launch_bounds__(256) finalize_candidates_kernel(const ScanParams p, const unsigned long long* __restrict__ cand,
+__global__ void __launch_bounds__(256, SMG_FINALIZE_MIN_BLOCKS) finalize_candidates_kernel(const ScanParams p, const unsigned long long* __restrict__ cand,
                                                                   const unsigned long long cand_cap, const int cand_shift,
                                                                   const double* __restrict__ thr64)
 {
@@ -842,7 +845,7 @@ int smg_scan_tc(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amas
     }
     // PWMs wider than the register / fragment kernels: emitted as candidates by a generic kernel? No -- scored directly.
     if (!s->wide.empty() && s->split == 0) return fail(SMG_ERR_UNSUPPORTED, "smg_scan_tc: PWMs wider than 32 need smg_scan");
-    finalize_candidates_kernel<<<148 * 8, 256, 0, st>>>(p, reinterpret_cast<const unsigned long long*>(d_cand), cand_cap,
+    finalize_candidates_kernel<<<148 * SMG_FINALIZE_MIN_BLOCKS * 2, 256, 0, st>>>(p, reinterpret_cast<const unsigned long long*>(d_cand), cand_cap,
                                                        hp.cand_shift, d_thr64);
     SMG_LAUNCH_CHECK("finalize_candidates_kernel");
     return SMG_OK;
