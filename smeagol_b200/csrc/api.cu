@@ -412,8 +412,13 @@ __global__ void __launch_bounds__(256, SMG_FINALIZE_MIN_BLOCKS) finalize_candida
     const unsigned long long n_cand = min(p.counters[SMG_CTR_CANDIDATES], cand_cap);
     const int key_shift = p.pos_bits + p.motif_bits;
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned long long n_round = (n_cand + 31ull) & ~31ull;  // whole warps stay convergent for the ballots
-    unsigned n_def = 0, n_near = 0, n_acc = 0;                      // per-thread tallies, one atomic per warp at the end
+    // whole blocks stay convergent: the hit list is extended with ONE atomic per block and iteration (the append counter
+    // is a single address; one atomic per warp serialised in the L2 atomic unit)
+    const unsigned long long n_round = (n_cand + 255ull) & ~255ull;
+    __shared__ unsigned s_cnt[8];
+    __shared__ unsigned long long s_base;
+    const unsigned warp = threadIdx.x >> 5;
+    unsigned n_def = 0, n_near = 0, n_acc = 0;  // per-thread tallies, one atomic per warp at the end
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         bool hit = false;
@@ -452,18 +457,23 @@ __global__ void __launch_bounds__(256, SMG_FINALIZE_MIN_BLOCKS) finalize_candida
         }
         if (p.hit_keys) {
             const unsigned m = __ballot_sync(SMG_FULL_MASK, hit);
-            if (m) {
-                unsigned long long base = 0;
-                if (lane == (unsigned)(__ffs((int)m) - 1)) base = atomicAdd(&p.counters[SMG_CTR_HITS_APPENDED], (unsigned long long)__popc(m));
-                base = __shfl_sync(SMG_FULL_MASK, base, __ffs((int)m) - 1);
-                if (hit) {
-                    const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
-                    if (slot < p.hit_cap) {
-                        p.hit_keys[slot] = key;
-                        p.hit_scores[slot] = s32;
-                    }
+            if (lane == 0) s_cnt[warp] = (unsigned)__popc(m);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned tot = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { const unsigned c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+                s_base = tot ? atomicAdd(&p.counters[SMG_CTR_HITS_APPENDED], (unsigned long long)tot) : 0ull;
+            }
+            __syncthreads();
+            if (hit) {
+                const unsigned long long slot = s_base + s_cnt[warp] + __popc(m & ((1u << lane) - 1u));
+                if (slot < p.hit_cap) {
+                    p.hit_keys[slot] = key;
+                    p.hit_scores[slot] = s32;
                 }
             }
+            __syncthreads();  // s_cnt / s_base are rewritten in the next iteration
         }
     }
     n_def = __reduce_add_sync(SMG_FULL_MASK, n_def);
