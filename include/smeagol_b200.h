@@ -99,6 +99,22 @@ int smg_pack(const uint8_t* d_src, int input_kind, const smg_row_t* d_rows, cons
              int32_t n_rows, int64_t total_words, uint32_t* d_packed, uint16_t* d_amask, uint8_t* d_codes,
              int64_t* d_status, void* stream);
 
+/* io.read_fasta (io.py:16-41, Biopython SeqIO.parse(handle, "fasta")) for the part that touches every byte, on the
+ * device ("next" row 8(f)-2: FASTA text -> per-record ASCII, which smg_pack then encodes).  d_bytes: the file's bytes
+ * (after gunzip), 16-byte aligned, n < 2^31.
+ * smg_fasta_index: offsets of the header lines ('>' as the first byte of a line), UNORDERED, into d_hdr_start;
+ *   *d_n_hdr = how many were found (> hdr_cap: call again with a larger buffer).  The caller sorts them.
+ * smg_fasta_compact: with the SORTED header offsets: d_hdr_end[r] = offset of the '\n' ending header r (or n);
+ *   d_seq_len[r] = bases of record r; d_out = the sequences of all records back to back in file order, with
+ *   '\n', '\r', ' ' and '\t' removed (record r starts at the exclusive prefix sum of d_seq_len); *d_n_out = their
+ *   total.  Bytes before the first header are ignored, as Biopython does.  upper != 0 maps a-z to A-Z on the fly
+ *   (the reference raises KeyError on lower case; soft-masked genomes need this).  d_bytes is MODIFIED (header lines
+ *   are blanked).  Temporary storage as in CUB: call with d_temp = NULL to get *temp_bytes. */
+int smg_fasta_index(const uint8_t* d_bytes, int64_t n, int64_t* d_hdr_start, uint64_t hdr_cap, uint64_t* d_n_hdr, void* stream);
+int smg_fasta_compact(uint8_t* d_bytes, int64_t n, const int64_t* d_hdr_start, int64_t n_hdr, int64_t* d_hdr_end,
+                      uint64_t* d_seq_len, uint8_t* d_out, int64_t* d_n_out, int upper, void* d_temp, uint64_t* temp_bytes,
+                      void* stream);
+
 /* PWMModel.predict_with_threshold (models.py:102-178) fused with the per-(row, motif, strand) counting of
  * scan._count_sites (scan.py:114-147): both strands, threshold, end trim, stream compaction, counts.
  *  d_thr_lo / d_thr_hi [n_motifs]: fp32 bounds of the near-threshold band; score > thr_hi is a definite hit,

@@ -514,6 +514,10 @@ static int upload(T** dptr, const std::vector<T>& h)
     return SMG_OK;
 }
 
+// used by the other translation units of the library (fasta.cu)
+int smg_fail_from(int code, const std::string& msg) { return fail(code, msg); }
+void smg_count_launch() { ++g_launches; }
+
 // ------------------------------------------------------------------------------------------ C ABI
 extern "C" {
 

@@ -510,3 +510,68 @@ def test_nonfinite_weights_never_hit_like_the_reference():
             res, exp = check_against_oracle(model, seqs, 0.5, "both")
             assert set(np.unique(exp["motif"])) == {0, 2, 4, 6}
             assert res.stats["n_near"] < 1000  # the dead PWMs are switched off, not sent to the adjudicator
+
+
+@pytest.mark.gpu
+def test_fasta_device_ingest_matches_host_parser(tmp_path):
+    """FASTA text -> packed SeqBatch on the device (csrc/fasta.cu) against the host parser that
+    mirrors io.read_fasta (io.py:16-41): same records, same de-wrapped sequences, same scan results.  Edge cases: text
+    before the first header, CRLF line ends, blank lines, blanks inside lines, '>' inside a sequence line, a header as
+    the last line, no trailing newline, short and long lines, many records (headers straddling 16-byte loads), gzip."""
+    sb = _sb()
+    from smeagol_b200 import device as dev
+    from smeagol_b200 import io as sio
+
+    rng = np.random.default_rng(53)
+    texts = []
+    texts.append("junk line\n>a first record\nACGT ACGT\r\nAC\n\n>b\nTTTT\n>c  two  spaces\nGATTACA")
+    parts = []
+    for i in range(300):  # many short records, line widths 1..90
+        L = int(rng.integers(1, 400))
+        s = rand_seq(rng, L, "ACGTN", [0.24, 0.24, 0.24, 0.24, 0.04])
+        w = int(rng.integers(1, 91))
+        eol = "\r\n" if i % 7 == 0 else "\n"
+        parts.append(">r%d len=%d%s" % (i, L, eol) + eol.join(s[j:j + w] for j in range(0, L, w)) + eol)
+    texts.append("".join(parts))
+    big = rand_seq(rng, 300_000)
+    texts.append(">chrBig\n" + "\n".join(big[j:j + 60] for j in range(0, len(big), 60)) + "\n>tail\nACGTACGTAC\n")
+    model = sb.models.PWMModel(synth_pwms(rng, 40, 5, 14))
+    for t, text in enumerate(texts):
+        for gz in (False, True):
+            path = str(tmp_path / ("f%d.fa%s" % (t, ".gz" if gz else "")))
+            if gz:
+                import gzip
+                with gzip.open(path, "wt", newline="") as fh:
+                    fh.write(text)
+            else:
+                with open(path, "w", newline="") as fh:
+                    fh.write(text)
+            host = sio.read_fasta(path)
+            fb = sio.read_fasta_device(path)
+            assert fb.ids == [r.id for r in host] and fb.names == [r.name for r in host]
+            assert fb.descriptions == [r.description for r in host]
+            assert list(fb.lengths) == [len(r.seq) for r in host]
+            assert [str(r.seq) for r in fb.records()] == [str(r.seq) for r in host]
+            if not gz:
+                seqs = [str(r.seq) for r in host]
+                keep = [i for i, s in enumerate(seqs) if len(s) > 0]
+                n = len(seqs)
+                out_rows = np.stack([np.arange(n), n + np.arange(n)], axis=1).astype(np.int32)
+                thr = model.thresholds(0.6)
+                a = dev.scan(model.device_set, fb.batch, thr, 3, out_rows, 2 * n)
+                b = dev.scan(model.device_set, dev.SeqBatch(seqs), thr, 3, out_rows, 2 * n)
+                assert a.n_hits == b.n_hits and len(keep) > 0
+                np.testing.assert_array_equal(a.keys[:a.n_hits].cpu().numpy(), b.keys[:b.n_hits].cpu().numpy())
+                np.testing.assert_array_equal(a.counts.cpu().numpy(), b.counts.cpu().numpy())
+    # lower case: KeyError like the reference unless upper=True
+    path = str(tmp_path / "lower.fa")
+    with open(path, "w") as fh:
+        fh.write(">x\nACGTacgtNNnn\nacgt\n")
+    with pytest.raises(KeyError):
+        sio.read_fasta_device(path)
+    fb = sio.read_fasta_device(path, upper=True)
+    assert [str(r.seq) for r in fb.records()] == ["ACGTACGTNNNNACGT"]
+    with pytest.raises(ValueError):
+        sio.read_fasta_device(None, data=b"no header here\nACGT\n")
+    with pytest.raises(KeyError, match=">"):  # '>' inside a line is sequence text: the encoder rejects it (encode.py:66)
+        sio.read_fasta_device(None, data=b">b\nTT>TT\n")

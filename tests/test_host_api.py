@@ -122,3 +122,18 @@ def test_chunks_and_row_layout_host_side():
     assert list(ch["row"]) == [0, 1, 2, 2, 3] and list(ch["start"]) == [0, 0, 0, 4096, 0]
     assert dev.pick_chunk_len(10_000_000, 32) == 4096 and dev.pick_chunk_len(30_000, 4) == 256
     assert dev._bits(1000) == 10 and dev._bits(1024) == 10 and dev._bits(1025) == 11 and dev._bits(1) == 1
+
+
+def test_read_fasta_host_semantics(tmp_path):
+    """io.read_fasta mirrors Biopython's FastaIterator (reference io.py:16-41): text before the first header is skipped,
+    id = name = first token, description = the whole header line, line breaks / blanks / carriage returns removed."""
+    from smeagol_b200 import io as sio
+
+    p = tmp_path / "a.fa"
+    p.write_bytes(b"junk\n>a first record\nACGT ACGT\r\nAC\n\n>b\nTTTT\n>c  two  spaces\nGATTACA")
+    recs = sio.read_fasta(str(p))
+    assert [(r.id, r.name, r.description, str(r.seq)) for r in recs] == [
+        ("a", "a", "a first record", "ACGTACGTAC"), ("b", "b", "b", "TTTT"), ("c", "c", "c  two  spaces", "GATTACA")]
+    sio.write_fasta(recs, str(tmp_path / "b.fa.gz"))
+    again = sio.read_fasta(str(tmp_path / "b.fa.gz"))
+    assert [str(r.seq) for r in again] == [str(r.seq) for r in recs] and [r.id for r in again] == ["a", "b", "c"]
