@@ -110,6 +110,15 @@ int smg_pack(const uint8_t* d_src, int input_kind, const smg_row_t* d_rows, cons
  *   total.  Bytes before the first header are ignored, as Biopython does.  upper != 0 maps a-z to A-Z on the fly
  *   (the reference raises KeyError on lower case; soft-masked genomes need this).  d_bytes is MODIFIED (header lines
  *   are blanked).  Temporary storage as in CUB: call with d_temp = NULL to get *temp_bytes. */
+/* utils.shuffle_records (utils.py:36-83) on the device ("next" row 8(f)-1): n_copies k-mer preserving shuffles of one
+ * sequence, all in one launch.  d_tok: the sequence as integer codes 0..16 (len bytes).  k = 2 (dinucleotide, the
+ * published algorithm of deeplift.dinuc_shuffle): d_succ = the successors tok[i+1] bucketed by tok[i] in original order
+ * (len - 1 bytes), d_off[18] = bucket offsets.  k = 1: uniform permutation (d_succ, d_off unused).  Output: ASCII, copy c
+ * at d_out + c * stride.  d_scratch (n_copies * len bytes) is only needed when len > 200 KiB (shared memory otherwise).
+ * Seeded and deterministic, but not numpy's / Python's random stream. */
+int smg_kmer_shuffle(const uint8_t* d_tok, int64_t len, const uint8_t* d_succ, const int64_t* d_off, int32_t n_copies, int32_t k,
+                     uint64_t seed, uint8_t* d_scratch, uint8_t* d_out, int64_t stride, void* stream);
+
 int smg_fasta_index(const uint8_t* d_bytes, int64_t n, int64_t* d_hdr_start, uint64_t hdr_cap, uint64_t* d_n_hdr, void* stream);
 int smg_fasta_compact(uint8_t* d_bytes, int64_t n, const int64_t* d_hdr_start, int64_t n_hdr, int64_t* d_hdr_end,
                       uint64_t* d_seq_len, uint8_t* d_out, int64_t* d_n_out, int upper, void* d_temp, uint64_t* temp_bytes,

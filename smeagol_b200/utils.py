@@ -58,20 +58,81 @@ def get_site_seq(site, seqs):
     return str(seq.seq[site.start:site.end])
 
 
-def shuffle_records(records, simN, simK=2, out_file=None, seed=1):
-    """Background generation (utils.py:36-83) is outside the accelerated path ("next" rank 1):
-    BASELINE config 3 uses fixed pre-generated shuffles.  Only the mononucleotide shuffle (simK=1), which needs no
-    third-party code, is provided; the dinucleotide shuffle of the reference lives in deeplift."""
-    import random
+def _successor_buckets(tok):
+    """Successors tok[i+1] bucketed by tok[i] in original order + bucket offsets (17 symbols): the per-symbol lists
+    that the dinucleotide shuffle permutes (deeplift.dinuc_shuffle's shuf_next_inds, as symbols instead of indices)."""
+    order = np.argsort(tok[:-1], kind="stable")
+    succ = np.ascontiguousarray(tok[1:][order])
+    off = np.zeros(18, dtype=np.int64)
+    off[1:] = np.cumsum(np.bincount(tok[:-1], minlength=17))
+    return succ, off
 
-    if simK != 1:
-        raise NotImplementedError("dinucleotide shuffling (deeplift.dinuc_shuffle) is out of scope; pass shuf_seqs")
-    shuf_records = []
-    for record in records:
-        seq = str(record.seq)
-        random.seed(seed)
-        for i in range(simN):
-            shuffled = list(seq)
-            random.shuffle(shuffled)
-            shuf_records.append(SeqRecord(Seq("".join(shuffled)), id="background_seq_{0:d}".format(i), name=record.id))
+
+def shuffle_batch_device(records, simN, simK=2, seed=1, device=None):
+    """simN k-mer preserving shuffles of every record, generated and packed on the GPU (csrc/shuffle.cu): the copies
+    never exist on the host.  Returns (ids, names, SeqBatch, ascii) with the reference's naming (utils.py:68-71):
+    id 'background_seq_i', name = the record's id; rows are ordered record by record, copy by copy.
+    Seeded and deterministic, but not the numpy / Python random stream of the reference."""
+    import torch
+
+    from . import _lib
+    from . import device as dev
+    from .encode import integer_encoding_dict
+
+    if simK not in (1, 2):
+        raise ValueError("simK must be 1 or 2.")
+    d = dev._require_cuda(device)
+    lib = _lib.load()
+    lut = np.full(256, 255, dtype=np.uint8)
+    for ch, code in integer_encoding_dict.items():
+        lut[ord(ch)] = code
+    ids, names, lens, outs = [], [], [], []
+    with torch.cuda.device(d):
+        for r, record in enumerate(records):
+            raw = np.frombuffer(str(record.seq).encode("ascii"), dtype=np.uint8)
+            tok = lut[raw]
+            if tok.size and tok.max() == 255:
+                raise KeyError(chr(int(raw[int(np.argmax(tok == 255))])))
+            L = int(tok.shape[0])
+            stride = (L + 15) // 16 * 16
+            d_out = torch.zeros(max(simN * stride, 16), dtype=torch.uint8, device=d)
+            if L > 0 and simN > 0:
+                d_tok = torch.from_numpy(tok.copy()).to(d)
+                if simK == 2 and L > 1:
+                    succ, off = _successor_buckets(tok)
+                    d_succ, d_off = torch.from_numpy(succ).to(d), torch.from_numpy(off).to(d)
+                else:
+                    d_succ = d_off = None
+                d_scr = torch.empty(simN * L, dtype=torch.uint8, device=d) if L > 200 * 1024 else None
+                k = simK if L > 1 else 1
+                _lib.check(lib.smg_kmer_shuffle(dev._ptr(d_tok), L, dev._ptr(d_succ), dev._ptr(d_off), simN, k,
+                                                (int(seed) * 0x9E3779B1 + r) & (2 ** 64 - 1), dev._ptr(d_scr), dev._ptr(d_out), stride,
+                                                dev._stream()), "smg_kmer_shuffle")
+            outs.append((d_out, stride, L))
+            ids += ["background_seq_{0:d}".format(i) for i in range(simN)]
+            names += [record.id] * simN
+            lens += [L] * simN
+        flat = torch.cat([o for o, _, _ in outs]) if len(outs) > 1 else outs[0][0]
+        src_off, base = [], 0
+        for o, stride, L in outs:
+            src_off += [base + i * stride for i in range(simN)]
+            base += int(o.numel())
+        batch = dev.SeqBatch(None, flat=(flat, np.asarray(src_off, dtype=np.int64), np.asarray(lens, dtype=np.int64)), device=d)
+    return ids, names, batch, (flat, np.asarray(src_off, dtype=np.int64), np.asarray(lens, dtype=np.int64))
+
+
+def shuffle_records(records, simN, simK=2, out_file=None, seed=1):
+    """Shuffle sequences conserving k-mer frequencies, k = 1 or 2 (utils.py:36-83; same signature, ids and names).
+    The copies are generated on the GPU (shuffle_batch_device) and read back as SeqRecords; use shuffle_batch_device
+    directly to keep them on the device.  simK = 2 is the algorithm of deeplift.dinuc_shuffle (every dinucleotide
+    count, the first and the last base are preserved), with a different, seeded random stream."""
+    ids, names, _, (flat, src_off, lens) = shuffle_batch_device(records, simN, simK, seed)
+    host = flat.cpu().numpy()
+    shuf_records = [SeqRecord(Seq(host[o:o + n].tobytes().decode("ascii")), id=i, name=m)
+                    for i, m, o, n in zip(ids, names, src_off, lens)]
+    print("Shuffled {} sequence(s) {} times while conserving k-mer frequency for k = {}.".format(len(records), simN, simK))
+    if out_file is not None:
+        from .io import write_fasta
+
+        write_fasta(shuf_records, out_file)
     return shuf_records

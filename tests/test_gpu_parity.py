@@ -575,3 +575,63 @@ def test_fasta_device_ingest_matches_host_parser(tmp_path):
         sio.read_fasta_device(None, data=b"no header here\nACGT\n")
     with pytest.raises(KeyError, match=">"):  # '>' inside a line is sequence text: the encoder rejects it (encode.py:66)
         sio.read_fasta_device(None, data=b">b\nTT>TT\n")
+
+
+@pytest.mark.gpu
+def test_kmer_shuffle_device_properties_and_distribution():
+    """utils.shuffle_records on the device.  Every copy must have the properties of the reference's
+    shuffles (utils.py:36-83; simK = 2 is deeplift.dinuc_shuffle's algorithm: all dinucleotide counts, first and last
+    base preserved; simK = 1: base counts), be reproducible from the seed, differ between copies and seeds, and sample
+    the same distribution as the CPU restatement (oracle/shuffle_oracle.py): compared on the per-position base
+    frequencies of a short sequence over many copies."""
+    sb = _sb()
+    from oracle import shuffle_oracle as sho
+    from smeagol_b200 import utils as su
+
+    rng = np.random.default_rng(59)
+    recs = [sb.SeqRecord(sb.Seq(rand_seq(rng, 3000)), id="g0", name="g0"),
+            sb.SeqRecord(sb.Seq(rand_seq(rng, 257, "ACGTN", [0.3, 0.2, 0.2, 0.25, 0.05])), id="g1", name="g1"),
+            sb.SeqRecord(sb.Seq("A"), id="g2", name="g2"), sb.SeqRecord(sb.Seq("ACGTTTGA"), id="g3", name="g3")]
+    for k in (1, 2):
+        out = su.shuffle_records(recs, 6, simK=k, seed=7)
+        assert [r.id for r in out] == ["background_seq_%d" % i for i in range(6)] * 4
+        assert [r.name for r in out] == ["g0"] * 6 + ["g1"] * 6 + ["g2"] * 6 + ["g3"] * 6
+        for i, r in enumerate(out):
+            sho.check_shuffle(str(recs[i // 6].seq), str(r.seq), k)
+        assert len({str(r.seq) for r in out[:6]}) == 6                       # copies differ
+        again = su.shuffle_records(recs, 6, simK=k, seed=7)
+        assert [str(r.seq) for r in again] == [str(r.seq) for r in out]      # seeded
+        other = su.shuffle_records(recs, 6, simK=k, seed=8)
+        assert [str(r.seq) for r in other[:6]] != [str(r.seq) for r in out[:6]]
+    # a long sequence takes the global-scratch path (> 200 KiB)
+    big = sb.SeqRecord(sb.Seq(rand_seq(rng, 300_000)), id="big", name="big")
+    for k in (1, 2):
+        o = su.shuffle_records([big], 2, simK=k, seed=3)
+        for r in o:
+            sho.check_shuffle(str(big.seq), str(r.seq), k)
+        assert str(o[0].seq) != str(o[1].seq)
+    # distribution: per-position base frequencies over many copies, device vs the CPU restatement of the algorithm
+    seq = "ACGTTGCAAGCTTAGGCTAACGTCAGT"
+    n = 4000
+    dev_copies = [str(r.seq) for r in su.shuffle_records([sb.SeqRecord(sb.Seq(seq), id="s", name="s")], n, simK=2, seed=11)]
+    rs = np.random.RandomState(5)
+    cpu_copies = [sho.dinuc_shuffle(seq, rs) for _ in range(n)]
+    for c in dev_copies[:50]:
+        sho.check_shuffle(seq, c, 2)
+
+    def freq(copies):
+        a = np.frombuffer("".join(copies).encode(), dtype=np.uint8).reshape(len(copies), len(seq))
+        return np.stack([(a == ord(b)).mean(axis=0) for b in "ACGT"])
+
+    assert np.abs(freq(dev_copies) - freq(cpu_copies)).max() < 0.05   # ~4 sigma of a binomial at n = 4000
+    assert len(set(dev_copies)) > 0.5 * len(set(cpu_copies))          # comparable diversity of Eulerian paths
+    # the packed batch scans like the read-back records
+    ids, names, batch, _ = su.shuffle_batch_device(recs[:2], 3, 2, seed=7)
+    back = su.shuffle_records(recs[:2], 3, simK=2, seed=7)
+    from smeagol_b200 import device as dev
+    model = sb.models.PWMModel(synth_pwms(rng, 20, 5, 12))
+    nrow = len(ids)
+    out_rows = np.stack([np.arange(nrow), nrow + np.arange(nrow)], axis=1).astype(np.int32)
+    a = dev.scan(model.device_set, batch, model.thresholds(0.6), 3, out_rows, 2 * nrow)
+    b = dev.scan(model.device_set, dev.SeqBatch([str(r.seq) for r in back]), model.thresholds(0.6), 3, out_rows, 2 * nrow)
+    np.testing.assert_array_equal(a.keys[:a.n_hits].cpu().numpy(), b.keys[:b.n_hits].cpu().numpy())
