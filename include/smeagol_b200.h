@@ -110,6 +110,13 @@ int smg_pack(const uint8_t* d_src, int input_kind, const smg_row_t* d_rows, cons
  *   total.  Bytes before the first header are ignored, as Biopython does.  upper != 0 maps a-z to A-Z on the fly
  *   (the reference raises KeyError on lower case; soft-masked genomes need this).  d_bytes is MODIFIED (header lines
  *   are blanked).  Temporary storage as in CUB: call with d_temp = NULL to get *temp_bytes. */
+/* scan._bin_sites_by_score (scan.py:77-111) on the device ("next" row 8(f)-3): histogram of frac_score =
+ * score / max_score (fp64) of a hit list (sorted or not) over right-closed bins (d_edges[b], d_edges[b+1]], b < n_bins
+ * (pd.cut semantics; d_edges has n_bins + 1 ascending entries).  d_hist[n_out_rows][n_motifs][n_bins] must be zeroed by
+ * the caller; hits outside (d_edges[0], d_edges[n_bins]] are not counted. */
+int smg_bin_hits(const uint64_t* d_keys, const float* d_scores, uint64_t n_hits, int pos_bits, int motif_bits,
+                 const double* d_max_scores, const double* d_edges, int32_t n_bins, int32_t n_motifs, int32_t* d_hist, void* stream);
+
 /* utils.shuffle_records (utils.py:36-83) on the device ("next" row 8(f)-1): n_copies k-mer preserving shuffles of one
  * sequence, all in one launch.  d_tok: the sequence as integer codes 0..16 (len bytes).  k = 2 (dinucleotide, the
  * published algorithm of deeplift.dinuc_shuffle): d_succ = the successors tok[i+1] bucketed by tok[i] in original order

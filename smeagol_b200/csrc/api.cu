@@ -486,6 +486,30 @@ __global__ void __launch_bounds__(256, SMG_FINALIZE_MIN_BLOCKS) finalize_candida
     }
 }
 
+// scan._bin_sites_by_score (scan.py:77-111) on the device: frac = score / max_score in fp64, pd.cut semantics
+// (right-closed intervals (e[b], e[b+1]]; values outside (e[0], e[n_bins]] fall in no bin), one histogram cell per
+// (output row, motif, bin).
+__global__ void __launch_bounds__(256) bin_hits_kernel(const unsigned long long* __restrict__ keys, const float* __restrict__ scores,
+                                                       const unsigned long long n_hits, const int pos_bits, const int motif_bits,
+                                                       const double* __restrict__ max_scores, const double* __restrict__ edges,
+                                                       const int n_bins, int* __restrict__ hist, const int n_motifs)
+{
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_hits;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long k = keys[i];
+        const int motif = (int)(k & ((1ull << motif_bits) - 1ull));
+        const long long row = (long long)(k >> (pos_bits + motif_bits));
+        const double frac = (double)scores[i] / max_scores[motif];
+        if (!(frac > edges[0]) || !(frac <= edges[n_bins])) continue;
+        int lo = 0, hi = n_bins - 1;  // largest b with edges[b] < frac
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (edges[mid] < frac) lo = mid; else hi = mid - 1;
+        }
+        atomicAdd(hist + ((size_t)row * n_motifs + motif) * n_bins + lo, 1);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host helpers
 static int init_lut()
 {
@@ -894,6 +918,21 @@ int smg_sort_hits(const uint64_t* d_keys_in, const float* d_scores_in, uint64_t*
                                                     (size_t)n, 0, key_bits, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(SMG_ERR_CUDA, std::string("cub::DeviceRadixSort: ") + cudaGetErrorString(e));
     if (!d_temp) *temp_bytes = (uint64_t)tb; else ++g_launches;
+    return SMG_OK;
+}
+
+int smg_bin_hits(const uint64_t* d_keys, const float* d_scores, uint64_t n_hits, int pos_bits, int motif_bits,
+                 const double* d_max_scores, const double* d_edges, int32_t n_bins, int32_t n_motifs, int32_t* d_hist, void* stream)
+{
+    if (!d_max_scores || !d_edges || n_bins <= 0 || n_motifs <= 0 || !d_hist || pos_bits <= 0 || motif_bits <= 0 ||
+        pos_bits + motif_bits > 63)
+        return fail(SMG_ERR_INVALID, "smg_bin_hits: bad argument");
+    if (n_hits == 0) return SMG_OK;
+    if (!d_keys || !d_scores) return fail(SMG_ERR_INVALID, "smg_bin_hits: hit list missing");
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n_hits + 255) / 256, 148 * 16);
+    bin_hits_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(d_keys), d_scores, n_hits,
+                                                              pos_bits, motif_bits, d_max_scores, d_edges, n_bins, d_hist, n_motifs);
+    SMG_LAUNCH_CHECK("bin_hits_kernel");
     return SMG_OK;
 }
 

@@ -135,7 +135,7 @@ def _bin_sites_by_score(encoding, model, thresholded, scores, bins):
     return result
 
 
-def _device_scan_groups(encoded, model, frac_threshold, want_hits, want_counts):
+def _device_scan_groups(encoded, model, frac_threshold, want_hits, want_counts, sort=True):
     """One fused device scan over every SeqEncoding group.  Returns (ScanResult, layout) where layout maps the
     device rows / output rows back to groups."""
     groups = encoded.seqs
@@ -159,11 +159,69 @@ def _device_scan_groups(encoded, model, frac_threshold, want_hits, want_counts):
     out_rows = np.array(out_rows, dtype=np.int32)
     batch = dev.SeqBatch(fwd, kind="ascii")
     res = dev.scan(model.device_set, batch, model.thresholds(frac_threshold), dev.STRANDS[rcomp], out_rows, base_out,
-                   want_hits=want_hits, want_counts=want_counts, adjudicate=model.adjudicate)
+                   want_hits=want_hits, want_counts=want_counts, adjudicate=model.adjudicate, sort=sort)
     model.last_scan_stats = res.stats
     layout = {"group_first_out": np.array(group_first_out + [base_out], dtype=np.int64), "out_rows": out_rows,
               "n_out": base_out}
     return res, layout
+
+
+def _melt_binned(hist, row_labels, model, edges):
+    """Frame of scan._bin_sites_by_score (scan.py:77-111) from a dense histogram `hist` (n_rows, n_motifs, n_bins) of one
+    group: the crosstab keeps the OBSERVED (Matrix_id, width) rows and the OBSERVED (id, name, sense, bin) columns,
+    zero-fills inside that rectangle, and melt walks sorted columns (outer) x sorted rows (inner); `bin` is the
+    ordered categorical of pd.cut's right-closed intervals."""
+    ids, names, senses = row_labels
+    keys = list(zip(ids, names, senses))
+    col_uniques = sorted(set(keys))
+    pos_of = {k: i for i, k in enumerate(col_uniques)}
+    col_codes = np.fromiter((pos_of[k] for k in keys), dtype=np.int64, count=len(keys))
+    agg = np.zeros((len(col_uniques),) + hist.shape[1:], dtype=np.int64)
+    np.add.at(agg, col_codes, hist)
+    cats = pd.IntervalIndex.from_breaks(np.asarray(edges, dtype=np.float64), closed="right")
+    cols = np.argwhere(agg.sum(axis=1) > 0)          # observed (label, bin) pairs, already in sorted order
+    keep_m = np.flatnonzero(agg.sum(axis=(0, 2)) > 0)
+    if cols.shape[0] == 0:
+        out = pd.DataFrame({k: [] for k in ["Matrix_id", "width", "id", "name", "sense"]})
+        out["bin"] = pd.Categorical.from_codes([], categories=cats, ordered=True)
+        out["num"] = np.zeros(0, dtype=np.int64)
+        return out
+    m_order = keep_m[np.argsort(_motif_rank(model)[keep_m], kind="stable")]
+    nm = len(m_order)
+    lab = np.repeat(cols[:, 0], nm)
+    out = pd.DataFrame({
+        "Matrix_id": _take(model.Matrix_ids, np.tile(m_order, cols.shape[0])),
+        "width": np.tile(model.widths[m_order], cols.shape[0]),
+        "id": _take([c[0] for c in col_uniques], lab),
+        "name": _take([c[1] for c in col_uniques], lab),
+        "sense": _take([c[2] for c in col_uniques], lab),
+    })
+    out["bin"] = pd.Categorical.from_codes(np.repeat(cols[:, 1], nm), categories=cats, ordered=True)
+    out["num"] = agg[cols[:, 0]][:, m_order, :][np.arange(cols.shape[0]), :, cols[:, 1]].reshape(-1)
+    return out
+
+
+def _binned_counts_device(res, layout, groups, model, bins):
+    """Binned counts of every group from the device hit list (smg_bin_hits): no per-hit data leaves the GPU."""
+    import torch
+
+    from . import _lib
+
+    edges = np.concatenate([np.asarray(bins, dtype=np.float64), [1.0]])
+    n_bins = len(edges) - 1
+    d = res.counts.device if res.counts is not None else res.keys.device
+    hist = torch.zeros((layout["n_out"], model.channels, n_bins), dtype=torch.int32, device=d)
+    if res.n_hits:
+        d_max = torch.from_numpy(np.asarray(model.max_scores, dtype=np.float64)).to(d)
+        d_edges = torch.from_numpy(edges).to(d)
+        with torch.cuda.device(d):
+            _lib.check(_lib.load().smg_bin_hits(dev._ptr(res.keys), dev._ptr(res.scores), res.n_hits, res.pos_bits, res.motif_bits,
+                                                dev._ptr(d_max), dev._ptr(d_edges), n_bins, model.channels, dev._ptr(hist),
+                                                dev._stream()), "smg_bin_hits")
+    h = hist.cpu().numpy().astype(np.int64)
+    gfo = layout["group_first_out"]
+    frames = [_melt_binned(h[gfo[gi]:gfo[gi + 1]], (g.ids, g.names, g.senses), model, edges) for gi, g in enumerate(groups)]
+    return pd.concat(frames).reset_index(drop=True)
 
 
 def _find_sites_in_groups(encoding, model, threshold, outputs=["sites"], score=False, combine_seqs=False, sep_ids=False,
@@ -180,12 +238,16 @@ def _find_sites_in_groups(encoding, model, threshold, outputs=["sites"], score=F
     groups = encoding.seqs
     want_sites = ("sites" in outputs) or binned
     want_counts = ("counts" in outputs) or ("stats" in outputs)
-    res, layout = _device_scan_groups(encoding, model, frac, want_hits=want_sites, want_counts=want_counts)
+    device_bins = binned and "sites" not in outputs  # histogram on the device: the hit list never leaves the GPU
+    res, layout = _device_scan_groups(encoding, model, frac, want_hits=want_sites, want_counts=want_counts,
+                                      sort=not device_bins)
     ids_all = np.concatenate([g.ids for g in groups]).astype(object)
     names_all = np.concatenate([g.names for g in groups]).astype(object)
     senses_all = np.concatenate([g.senses for g in groups]).astype(object)
     output = {}
-    if want_sites:
+    if device_bins:
+        output["binned_counts"] = _binned_counts_device(res, layout, groups, model, threshold)
+    elif want_sites:
         row, pos, motif, sc = res.hits_host()
         if binned:
             gfo = layout["group_first_out"]

@@ -635,3 +635,24 @@ def test_kmer_shuffle_device_properties_and_distribution():
     a = dev.scan(model.device_set, batch, model.thresholds(0.6), 3, out_rows, 2 * nrow)
     b = dev.scan(model.device_set, dev.SeqBatch([str(r.seq) for r in back]), model.thresholds(0.6), 3, out_rows, 2 * nrow)
     np.testing.assert_array_equal(a.keys[:a.n_hits].cpu().numpy(), b.keys[:b.n_hits].cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_binned_counts_on_device_equal_host_route():
+    """outputs=['binned_counts'] alone is histogrammed on the device (smg_bin_hits, no hit leaves the
+    GPU); asking for the sites as well takes the reference's per-hit pd.cut + crosstab on the host.  Same frames."""
+    sb = _sb()
+    rng = np.random.default_rng(61)
+    model = sb.models.PWMModel(synth_pwms(rng, 30, 5, 14))
+    recs = [sb.SeqRecord(sb.Seq(rand_seq(rng, int(L))), id="s%d" % i, name="g%d" % (i % 2))
+            for i, L in enumerate([1500, 900, 1500, 900])]  # records sharing a name must have equal lengths (encode.py:172)
+    bins = np.array([0.5, 0.6, 0.7, 0.8, 0.95])
+    for kw in (dict(sense="+", rcomp="both"), dict(sense="-", rcomp="only", group_by="name"),
+               dict(sense="+", rcomp="both", group_by="name", combine_seqs=True, sep_ids=True),
+               dict(sense="+", rcomp="none", combine_seqs=True)):
+        a = sb.scan.scan_sequences(recs, model, bins, outputs=["binned_counts"], **kw)["binned_counts"]
+        b = sb.scan.scan_sequences(recs, model, bins, outputs=["binned_counts", "sites"], **kw)["binned_counts"]
+        assert list(a.columns) == list(b.columns) and len(a) == len(b) and len(a) > 0
+        for col in a.columns:
+            assert [str(x) for x in a[col]] == [str(x) for x in b[col]], (kw, col)
+        assert int(a.num.sum()) == int(b.num.sum())

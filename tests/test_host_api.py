@@ -137,3 +137,75 @@ def test_read_fasta_host_semantics(tmp_path):
     sio.write_fasta(recs, str(tmp_path / "b.fa.gz"))
     again = sio.read_fasta(str(tmp_path / "b.fa.gz"))
     assert [str(r.seq) for r in again] == [str(r.seq) for r in recs] and [r.id for r in again] == ["a", "b", "c"]
+
+
+def test_shuffle_oracle_and_successor_buckets():
+    """The CPU restatement of deeplift.dinuc_shuffle's algorithm keeps its defining properties, and the host pre-pass
+    of the device shuffle (successors bucketed by symbol, original order) matches a direct construction."""
+    from oracle import shuffle_oracle as sho
+    from smeagol_b200 import utils as su
+    from smeagol_b200.encode import integer_encoding_dict
+
+    rng = np.random.default_rng(3)
+    seq = "".join(rng.choice(list("ACGTN"), size=500, p=[0.3, 0.2, 0.2, 0.25, 0.05]))
+    rs = np.random.RandomState(1)
+    copies = [sho.dinuc_shuffle(seq, rs) for _ in range(5)]
+    for c in copies:
+        sho.check_shuffle(seq, c, 2)
+    assert len(set(copies)) == 5 and seq not in copies
+    tok = np.array([integer_encoding_dict[b] for b in seq], dtype=np.uint8)
+    succ, off = su._successor_buckets(tok)
+    assert off[0] == 0 and off[-1] == len(seq) - 1
+    for t in range(17):
+        want = [tok[i + 1] for i in range(len(seq) - 1) if tok[i] == t]
+        assert list(succ[off[t]:off[t + 1]]) == want
+    with pytest.raises(AssertionError):
+        sho.check_shuffle(seq, seq[::-1] if seq[::-1] != seq else seq + "A", 2)
+
+
+def test_melt_binned_equals_crosstab_of_hits():
+    """The dense-histogram route of the binned counts (device smg_bin_hits -> scan._melt_binned) builds the same frame
+    as the reference's per-hit pd.cut + crosstab + melt (scan.py:77-111), including which rows / columns exist."""
+    import pandas as pd
+
+    from smeagol_b200 import scan as sscan
+
+    class M:
+        pass
+
+    rng = np.random.default_rng(5)
+    model = M()
+    model.channels = 7
+    model.Matrix_ids = np.array(["m%d" % (i % 5) for i in range(7)], dtype=object)
+    model.widths = np.array([5, 7, 5, 9, 6, 8, 5])
+    model.max_scores = rng.uniform(5, 12, size=7)
+
+    class E:
+        pass
+
+    enc = E()
+    enc.ids = np.array(["a", "b", "a", "c", "b", "d"], dtype=object)
+    enc.names = np.array(["a", "b", "a", "c", "b", "d"], dtype=object)
+    enc.senses = np.array(["+", "+", "-", "+", "-", "+"], dtype=object)
+    bins = np.array([0.5, 0.6, 0.75, 0.9])
+    edges = np.concatenate([bins, [1.0]])
+    for n_hits, motifs in ((400, range(7)), (12, (1, 4)), (0, ())):
+        seq_idx = rng.integers(0, 5, size=n_hits)          # row 5 ('d') never hit
+        pwm_idx = rng.choice(list(motifs), size=n_hits) if n_hits else np.zeros(0, dtype=np.int64)
+        frac = rng.uniform(0.5001, 0.8999, size=n_hits)    # last bin never observed
+        scores = (frac * model.max_scores[pwm_idx]).astype(np.float32)
+        frac_used = scores / model.max_scores[pwm_idx]
+        hist = np.zeros((6, 7, 4), dtype=np.int64)
+        b = np.searchsorted(edges, frac_used, side="left") - 1
+        ok = (frac_used > edges[0]) & (frac_used <= edges[-1])
+        np.add.at(hist, (seq_idx[ok], pwm_idx[ok], b[ok]), 1)
+        got = sscan._melt_binned(hist, (enc.ids, enc.names, enc.senses), model, edges)
+        if n_hits == 0:
+            assert len(got) == 0 and list(got.columns) == ["Matrix_id", "width", "id", "name", "sense", "bin", "num"]
+            continue
+        want = sscan._bin_sites_by_score(enc, model, (seq_idx, np.zeros(n_hits, dtype=np.int64), pwm_idx), scores, bins)
+        assert list(got.columns) == list(want.columns) and len(got) == len(want)
+        for col in ("Matrix_id", "width", "id", "name", "sense", "num"):
+            assert list(got[col]) == list(want[col]), col
+        assert [str(x) for x in got["bin"]] == [str(x) for x in want["bin"]]
+        assert list(got["bin"].cat.categories) == list(want["bin"].cat.categories)
