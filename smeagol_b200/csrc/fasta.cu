@@ -13,7 +13,7 @@
 #include <string>
 
 #include <cub/device/device_select.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
+#include <thrust/iterator/transform_iterator.h>
 #include <cuda_runtime.h>
 
 #include "../../include/smeagol_b200.h"
@@ -181,7 +181,7 @@ int smg_fasta_compact(uint8_t* d_bytes, int64_t n, const int64_t* d_hdr_start, i
     if (n >= (1ll << 31)) return smg_fail_from(SMG_ERR_UNSUPPORTED, "smg_fasta_compact: at most 2^31 - 1 bytes per call");
     cudaStream_t st = (cudaStream_t)stream;
     size_t tb = d_temp ? (size_t)*temp_bytes : 0;
-    cub::TransformInputIterator<uint8_t, UpperOp, const uint8_t*> up_it(d_bytes, UpperOp());
+    thrust::transform_iterator<UpperOp, const uint8_t*> up_it((const uint8_t*)d_bytes, UpperOp());
     cudaError_t e;
     if (!d_temp) {  // size query
         e = upper ? cub::DeviceSelect::If(nullptr, tb, up_it, d_out, d_n_out, (int)n, KeepOp(), st)

@@ -166,7 +166,6 @@ __global__ void __launch_bounds__(32) __maxnreg__((HmmaMaxRegs<KS, NB>::v)) scan
     __shared__ uint32_t s_q[kTcQueue * 32];  // per-lane candidate queues, [slot][lane]
     static_assert(4 * NB <= kTcQueue - 8, "a tile must fit in the queue");
     const int lane = threadIdx.x;
-    const unsigned lt_mask = (1u << lane) - 1u;
     const int colgroup = hp.first_colgroup + blockIdx.y;
     const smg_chunk_t ch = p.chunks[blockIdx.x];
     const smg_row_t row = p.rows[ch.row];
@@ -195,7 +194,6 @@ __global__ void __launch_bounds__(32) __maxnreg__((HmmaMaxRegs<KS, NB>::v)) scan
     const int n = lane >> 2;         // position offset of this lane's B-fragment column within a tile
     const int kk = (lane & 3) >> 1;  // PWM-row offset of its k-pair within a k16 slice (second register: +2)
     const int bb = (lane & 1) * 2;   // its base pair {bb, bb+1}
-    const int q2 = (lane & 3) * 2;   // accumulator columns: positions pt + q2, pt + q2 + 1
     const uint32_t* __restrict__ wp = p.packed + row.word_off;
     const uint16_t* __restrict__ ap = p.amask + row.word_off;
     const unsigned long long rowbits = (unsigned long long)(unsigned)ch.row << hp.cand_shift;

@@ -333,7 +333,6 @@ __global__ void __launch_bounds__(32) __maxnreg__((MaxRegs<WB, NM>::v)) scan_reg
 #pragma unroll
                 for (int m = 0; m < NM; ++m) any_c = any_c || (fmaxf(o[m][0].x, o[m][0].y) > thr_lo[m]);
                 if (__any_sync(SMG_FULL_MASK, any_c)) {
-#pragma unroll
                     const unsigned tag0 = (unsigned)(wi * 16 + j) << 2;
 #pragma unroll
                     for (int m = 0; m < NM; ++m) {

@@ -104,8 +104,8 @@ __global__ void __launch_bounds__(32) variant_regtab_kernel(const VariantParams 
             if (pass == 1) {  // substitute the alternate base at fed index WB-1
                 const unsigned long long a2 = (unsigned long long)(alt == 5 ? 3 : alt - 1);
                 constexpr int idx = WB - 1;
-                if (idx < 32) L0 = (L0 & ~(3ull << (2 * idx))) | (a2 << (2 * idx));
-                else H0 = (H0 & ~(3ull << (2 * (idx - 32)))) | (a2 << (2 * (idx - 32)));
+                if constexpr (idx < 32) L0 = (L0 & ~(3ull << (2 * idx))) | (a2 << (2 * idx));
+                else H0 = (H0 & ~(3ull << (2 * (idx & 31)))) | (a2 << (2 * (idx & 31)));
             }
             V r[WB - 1];
 #pragma unroll
