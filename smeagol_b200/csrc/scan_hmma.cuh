@@ -11,7 +11,8 @@
 //
 // fp16 weights cannot give the reference's fp32 scores, so this kernel is only a FILTER: it emits every cell whose
 // approximate score exceeds (threshold - margin), margin = 2^-9 * sum_k max_b |T[k][b]| (>= 4x the fp16 rounding error
-// of the operands), as a 64-bit candidate (row, start, motif, strand).  finalize_candidates_kernel (api.cu) then
+// of the operands), as a 64-bit candidate (row, start, motif, strand): per-lane queues of 32-bit tags in shared memory
+// (predicated store + pointer bump in the loop), drained with ballot compaction.  finalize_candidates_kernel (api.cu) then
 // re-scores each candidate in fp32 in the SAME fixed order as the register-table kernel, adjudicates the near-threshold
 // band in fp64, and produces hits / counts that are bit-identical to the register-table path.
 #pragma once
@@ -146,9 +147,6 @@ static __device__ __noinline__ int drain_queues(const uint32_t* s_q, const int q
     return nst;
 }
 
-// KS = k16 steps (padded width = 4 * KS), NB = 16-column blocks per warp.  One warp per CTA; the warp walks its chunk
-// in tiles of 8 positions: B fragments for the next tile are generated (ALU) while the tensor pipe works on the
-// current one.
 // register caps on the occupancy steps of an SM sub-partition (see scan_regtab.cuh): 80/96/128/168 registers =
 // 6/5/4/3 one-warp CTAs
 template <int KS, int NB> struct HmmaMaxRegs {
@@ -158,6 +156,9 @@ template <int KS, int NB> struct HmmaMaxRegs {
                                        : (KS == 1 ? 64 : KS == 2 ? 72 : KS == 3 ? 80 : 128);
 };
 
+// KS = k16 steps (padded width = 4 * KS), NB = 16-column blocks per warp.  One warp per CTA; the warp walks its chunk
+// in tiles of 8 positions: the B fragments of the next tile are generated (integer pipe) while the tensor pipe works on
+// the current one; a tile that passes the vote pushes its candidates to per-lane queues, drained out of line.
 template <int KS, int NB>
 __global__ void __launch_bounds__(32) __maxnreg__((HmmaMaxRegs<KS, NB>::v)) scan_hmma_kernel(const HmmaParams hp)
 {
