@@ -77,7 +77,7 @@ class SeqEncoding:
     def __init__(self, records, rcomp="none", sense=None):
         if type(records) == str:  # the reference intends this (encode.py:124 compares against the string "str")
             records = read_fasta(records)
-        self.records = [seq_str(r) for r in records]
+        self.records = [seq_str(r, keep_device=True) for r in records]  # str, or DeviceSeq for device-resident records
         self._check_equal_lens(self.records)
         self.len = len(self.records[0])
         self.n_records = len(self.records)
@@ -105,9 +105,9 @@ class SeqEncoding:
         if self._seqs is None:
             rows = []
             if self.rcomp in ("none", "both"):
-                rows += [integer_encode(s, rc=False) for s in self.records]
+                rows += [integer_encode(str(s), rc=False) for s in self.records]
             if self.rcomp in ("only", "both"):
-                rows += [integer_encode(s, rc=True) for s in self.records]
+                rows += [integer_encode(str(s), rc=True) for s in self.records]
             self._seqs = np.vstack(rows)
         return self._seqs
 

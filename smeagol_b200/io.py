@@ -70,9 +70,11 @@ class FastaBatch:
         return len(self.ids)
 
     def records(self):
-        """Materialise SeqRecords on the host (D2H of the de-wrapped sequences) -- for callers of the reference API."""
-        flat = self._ascii.cpu().numpy()
-        return [SeqRecord(Seq(flat[o:o + n].tobytes().decode("ascii")), id=i, name=m, description=d)
+        """SeqRecords for callers of the reference API (scan_sequences, enrich_in_genome, ...): their sequences stay on
+        the device (seqrecord.DeviceSeq) and are read back only when their text is asked for."""
+        from .seqrecord import DeviceSeq
+
+        return [SeqRecord(DeviceSeq(self._ascii, o, n), id=i, name=m, description=d)
                 for i, m, d, o, n in zip(self.ids, self.names, self.descriptions, self._src_off, self.lengths)]
 
 

@@ -157,7 +157,14 @@ def _device_scan_groups(encoded, model, frac_threshold, want_hits, want_counts, 
                 out_rows.append((base_out + i, base_out + n + i))
         base_out += len(g.ids)
     out_rows = np.array(out_rows, dtype=np.int32)
-    batch = dev.SeqBatch(fwd, kind="ascii")
+    from .seqrecord import DeviceSeq
+
+    if fwd and all(isinstance(f, DeviceSeq) for f in fwd) and all(f.flat is fwd[0].flat for f in fwd):
+        # device-resident records (GPU shuffles, device FASTA ingest): pack straight from their buffer
+        batch = dev.SeqBatch(None, flat=(fwd[0].flat, np.array([f.offset for f in fwd], dtype=np.int64),
+                                         np.array([f.length for f in fwd], dtype=np.int64)), device=fwd[0].flat.device)
+    else:
+        batch = dev.SeqBatch([str(f) if isinstance(f, DeviceSeq) else f for f in fwd], kind="ascii")
     res = dev.scan(model.device_set, batch, model.thresholds(frac_threshold), dev.STRANDS[rcomp], out_rows, base_out,
                    want_hits=want_hits, want_counts=want_counts, adjudicate=model.adjudicate, sort=sort)
     model.last_scan_stats = res.stats

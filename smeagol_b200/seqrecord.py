@@ -62,5 +62,41 @@ except Exception:  # Biopython absent
             return "SeqRecord(seq=%r, id=%r, name=%r)" % (self.seq, self.id, self.name)
 
 
+class DeviceSeq(object):
+    """A sequence that lives in a device ASCII buffer (produced by the GPU shuffle / FASTA ingest).  Behaves like a Seq
+    for the reference API -- len(), str(), slicing, reverse_complement() read the bases back on demand -- while the scan
+    path recognises it and packs it on the device without a host round trip (scan._device_scan_groups)."""
+
+    def __init__(self, flat, offset, length):
+        self.flat, self.offset, self.length = flat, int(offset), int(length)
+        self._host = None
+
+    def __len__(self):
+        return self.length
+
+    def __str__(self):
+        if self._host is None:
+            self._host = self.flat[self.offset:self.offset + self.length].cpu().numpy().tobytes().decode("ascii")
+        return self._host
+
+    def __repr__(self):
+        return "DeviceSeq(length=%d, device=%s)" % (self.length, self.flat.device)
+
+    def __iter__(self):
+        return iter(str(self))
+
+    def __getitem__(self, i):
+        return Seq(str(self)[i]) if isinstance(i, slice) else str(self)[i]
+
+    def __eq__(self, other):
+        return str(self) == str(other)
+
+    def __hash__(self):
+        return hash((id(self.flat), self.offset, self.length))
+
+    def reverse_complement(self):
+        return Seq(str(self)).reverse_complement()
+
+
 def is_record(x):
     return hasattr(x, "seq") and hasattr(x, "id")

@@ -2,7 +2,7 @@
 import numpy as np
 
 from .io import read_fasta
-from .seqrecord import Seq, SeqRecord, is_record
+from .seqrecord import DeviceSeq, Seq, SeqRecord, is_record
 
 
 def _equals(x, y, eps=1e-4):
@@ -28,10 +28,16 @@ def get_Seq(seq):
     raise TypeError("Input sequence must be a string, Seqrecord or Seq object.")
 
 
-def seq_str(seq):
-    """Forward string of a str / Seq / SeqRecord."""
+def seq_str(seq, keep_device=False):
+    """Forward string of a str / Seq / SeqRecord (keep_device: a device-resident sequence is returned as it is)."""
     if type(seq) == str:
         return seq
+    if keep_device and isinstance(seq, DeviceSeq):
+        return seq
+    if keep_device and is_record(seq) and isinstance(seq.seq, DeviceSeq):
+        return seq.seq
+    if isinstance(seq, DeviceSeq):
+        return str(seq)
     if is_record(seq):
         return str(seq.seq)
     if isinstance(seq, Seq):
@@ -123,13 +129,13 @@ def shuffle_batch_device(records, simN, simK=2, seed=1, device=None):
 
 def shuffle_records(records, simN, simK=2, out_file=None, seed=1):
     """Shuffle sequences conserving k-mer frequencies, k = 1 or 2 (utils.py:36-83; same signature, ids and names).
-    The copies are generated on the GPU (shuffle_batch_device) and read back as SeqRecords; use shuffle_batch_device
-    directly to keep them on the device.  simK = 2 is the algorithm of deeplift.dinuc_shuffle (every dinucleotide
+    The copies are generated on the GPU (shuffle_batch_device); the returned SeqRecords hold device-resident sequences
+    (seqrecord.DeviceSeq) that are read back only when a caller asks for their text.  simK = 2 is the algorithm of deeplift.dinuc_shuffle (every dinucleotide
     count, the first and the last base are preserved), with a different, seeded random stream."""
     ids, names, _, (flat, src_off, lens) = shuffle_batch_device(records, simN, simK, seed)
-    host = flat.cpu().numpy()
-    shuf_records = [SeqRecord(Seq(host[o:o + n].tobytes().decode("ascii")), id=i, name=m)
-                    for i, m, o, n in zip(ids, names, src_off, lens)]
+    # the copies stay on the device: .seq is a DeviceSeq (str() / len() / slicing read it back on demand), and
+    # scan_sequences packs such records without a host round trip
+    shuf_records = [SeqRecord(DeviceSeq(flat, o, n), id=i, name=m) for i, m, o, n in zip(ids, names, src_off, lens)]
     print("Shuffled {} sequence(s) {} times while conserving k-mer frequency for k = {}.".format(len(records), simN, simK))
     if out_file is not None:
         from .io import write_fasta

@@ -656,3 +656,43 @@ def test_binned_counts_on_device_equal_host_route():
         for col in a.columns:
             assert [str(x) for x in a[col]] == [str(x) for x in b[col]], (kw, col)
         assert int(a.num.sum()) == int(b.num.sum())
+
+
+@pytest.mark.gpu
+def test_device_resident_records_through_the_reference_api(tmp_path):
+    """Records produced on the device (GPU shuffles, device FASTA ingest) carry DeviceSeq sequences: scan_sequences /
+    enrich_in_genome pack them without a host round trip and return the same frames as for host strings; str(), len(),
+    slicing and reverse_complement() still work for callers that want the text."""
+    sb = _sb()
+    from smeagol_b200 import io as sio
+    from smeagol_b200 import utils as su
+    from smeagol_b200.seqrecord import DeviceSeq
+
+    rng = np.random.default_rng(67)
+    model = sb.models.PWMModel(synth_pwms(rng, 25, 5, 13))
+    genome = [sb.SeqRecord(sb.Seq(rand_seq(rng, 4000)), id="virus", name="virus")]
+    shuf = su.shuffle_records(genome, 12, simK=2, seed=5)
+    assert all(isinstance(r.seq, DeviceSeq) for r in shuf) and len(shuf[0]) == 4000
+    host = [sb.SeqRecord(sb.Seq(str(r.seq)), id=r.id, name=r.name) for r in shuf]
+    assert str(shuf[3].seq[10:20]) == str(host[3].seq)[10:20]
+    assert str(shuf[3].seq.reverse_complement()) == str(host[3].seq.reverse_complement())
+    kw = dict(sense="+", rcomp="both", outputs=["sites", "counts", "stats"], group_by="name", combine_seqs=True, sep_ids=True)
+    a = sb.scan.scan_sequences(shuf, model, 0.7, **kw)
+    b = sb.scan.scan_sequences(host, model, 0.7, **kw)
+    for k in ("sites", "counts", "stats"):
+        pd.testing.assert_frame_equal(a[k].reset_index(drop=True), b[k].reset_index(drop=True))
+    # enrichment with backgrounds generated on the device == the same call on their host copies
+    e1 = sb.enrich.enrich_in_genome(genome, model, "both", 0.7, simN=12, simK=2, shuf_seqs=shuf)
+    e2 = sb.enrich.enrich_in_genome(genome, model, "both", 0.7, simN=12, simK=2, shuf_seqs=host)
+    pd.testing.assert_frame_equal(e1["enrichment"].reset_index(drop=True), e2["enrichment"].reset_index(drop=True))
+    e3 = sb.enrich.enrich_in_genome(genome, model, "both", 0.7, simN=12, simK=2)  # default path: shuffles on the GPU
+    assert list(e3["enrichment"].columns) == list(e1["enrichment"].columns) and len(e3["shuf_stats"]) > 0
+    # device FASTA ingest -> records -> scan_sequences
+    path = str(tmp_path / "g.fa")
+    sio.write_fasta(genome + host[:3], path, gz=False)
+    fb = sio.read_fasta_device(path)
+    recs = fb.records()
+    assert all(isinstance(r.seq, DeviceSeq) for r in recs)
+    c = sb.scan.scan_sequences(recs, model, 0.7, sense="+", rcomp="both", outputs=["sites"], score=True)["sites"]
+    d = sb.scan.scan_sequences(sio.read_fasta(path), model, 0.7, sense="+", rcomp="both", outputs=["sites"], score=True)["sites"]
+    pd.testing.assert_frame_equal(c.reset_index(drop=True), d.reset_index(drop=True))
