@@ -209,3 +209,25 @@ def test_melt_binned_equals_crosstab_of_hits():
             assert list(got[col]) == list(want[col]), col
         assert [str(x) for x in got["bin"]] == [str(x) for x in want["bin"]]
         assert list(got["bin"].cat.categories) == list(want["bin"].cat.categories)
+
+
+def test_device_seq_behaves_like_a_seq():
+    """seqrecord.DeviceSeq (sequences that live in a device ASCII buffer) keeps the Seq behaviour the reference API
+    relies on; exercised here on a CPU tensor, the buffer type does not matter for the host-side logic."""
+    import torch
+
+    import smeagol_b200 as sb
+    from smeagol_b200.seqrecord import DeviceSeq
+    from smeagol_b200.utils import seq_str
+
+    flat = torch.from_numpy(np.frombuffer(b"NNACGTTGCAAGNN", dtype=np.uint8).copy())
+    s = DeviceSeq(flat, 2, 10)
+    assert len(s) == 10 and str(s) == "ACGTTGCAAG" and s[0] == "A" and str(s[2:5]) == "GTT"
+    assert str(s.reverse_complement()) == "CTTGCAACGT" and s == sb.Seq("ACGTTGCAAG") and list(s)[:3] == ["A", "C", "G"]
+    rec = sb.SeqRecord(s, id="x", name="x")
+    assert len(rec) == 10 and seq_str(rec) == "ACGTTGCAAG" and seq_str(rec, keep_device=True) is s
+    enc = sb.encode.SeqEncoding([rec, sb.SeqRecord(sb.Seq("ACGTACGTAC"), id="y", name="y")], rcomp="both", sense="+")
+    assert enc.len == 10 and enc.seqs.shape == (4, 10) and enc.records[0] is s
+    assert list(enc.seqs[0][:4]) == [1, 2, 3, 4]
+    with pytest.raises(ValueError):
+        sb.encode.SeqEncoding([rec, sb.SeqRecord(sb.Seq("ACG"), id="z", name="z")], rcomp="none", sense="+")
