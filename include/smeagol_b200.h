@@ -27,7 +27,7 @@ extern "C" {
 #define SMG_ERR_CUDA 2         /* a CUDA runtime call failed */
 #define SMG_ERR_UNSUPPORTED 3  /* e.g. no sm_100 device */
 
-#define SMG_MAX_REGTAB_WIDTH 32 /* wider PWMs go through the shared-memory gather kernel */
+#define SMG_MAX_REGTAB_WIDTH 32 /* wider PWMs go through scan_wide_kernel (one thread per window start, tables from global memory) */
 #define SMG_STRAND_FWD 1
 #define SMG_STRAND_RC 2
 
@@ -66,6 +66,8 @@ typedef struct {
 #define SMG_CTR_ADJ_ACCEPTED 3  /* near-threshold candidates accepted by the fp64 adjudicator */
 #define SMG_CTR_LAUNCHES 4      /* kernel launches issued by the library on behalf of this counter block */
 #define SMG_CTR_CANDIDATES 5    /* smg_scan_tc: candidates emitted by the tensor-core prefilter (> cand_cap: overflow) */
+#define SMG_CTR_NEAR_TC 6       /* smg_scan_tc: near-threshold candidates adjudicated inside its exact pass (a tally: they
+                                   never occupy d_near, so they do not count against near_cap) */
 #define SMG_N_COUNTERS 8
 
 int smg_version(void);
@@ -99,17 +101,6 @@ int smg_pack(const uint8_t* d_src, int input_kind, const smg_row_t* d_rows, cons
              int32_t n_rows, int64_t total_words, uint32_t* d_packed, uint16_t* d_amask, uint8_t* d_codes,
              int64_t* d_status, void* stream);
 
-/* io.read_fasta (io.py:16-41, Biopython SeqIO.parse(handle, "fasta")) for the part that touches every byte, on the
- * device ("next" row 8(f)-2: FASTA text -> per-record ASCII, which smg_pack then encodes).  d_bytes: the file's bytes
- * (after gunzip), 16-byte aligned, n < 2^31.
- * smg_fasta_index: offsets of the header lines ('>' as the first byte of a line), UNORDERED, into d_hdr_start;
- *   *d_n_hdr = how many were found (> hdr_cap: call again with a larger buffer).  The caller sorts them.
- * smg_fasta_compact: with the SORTED header offsets: d_hdr_end[r] = offset of the '\n' ending header r (or n);
- *   d_seq_len[r] = bases of record r; d_out = the sequences of all records back to back in file order, with
- *   '\n', '\r', ' ' and '\t' removed (record r starts at the exclusive prefix sum of d_seq_len); *d_n_out = their
- *   total.  Bytes before the first header are ignored, as Biopython does.  upper != 0 maps a-z to A-Z on the fly
- *   (the reference raises KeyError on lower case; soft-masked genomes need this).  d_bytes is MODIFIED (header lines
- *   are blanked).  Temporary storage as in CUB: call with d_temp = NULL to get *temp_bytes. */
 /* scan._bin_sites_by_score (scan.py:77-111) on the device ("next" row 8(f)-3): histogram of frac_score =
  * score / max_score (fp64) of a hit list (sorted or not) over right-closed bins (d_edges[b], d_edges[b+1]], b < n_bins
  * (pd.cut semantics; d_edges has n_bins + 1 ascending entries).  d_hist[n_out_rows][n_motifs][n_bins] must be zeroed by
@@ -126,6 +117,17 @@ int smg_bin_hits(const uint64_t* d_keys, const float* d_scores, uint64_t n_hits,
 int smg_kmer_shuffle(const uint8_t* d_tok, int64_t len, const uint8_t* d_succ, const int64_t* d_off, int32_t n_copies, int32_t k,
                      uint64_t seed, uint8_t* d_scratch, uint8_t* d_out, int64_t stride, void* stream);
 
+/* io.read_fasta (io.py:16-41, Biopython SeqIO.parse(handle, "fasta")) for the part that touches every byte, on the
+ * device ("next" row 8(f)-2: FASTA text -> per-record ASCII, which smg_pack then encodes).  d_bytes: the file's bytes
+ * (after gunzip), 16-byte aligned, n < 2^31.
+ * smg_fasta_index: offsets of the header lines ('>' as the first byte of a line), UNORDERED, into d_hdr_start;
+ *   *d_n_hdr = how many were found (> hdr_cap: call again with a larger buffer).  The caller sorts them.
+ * smg_fasta_compact: with the SORTED header offsets: d_hdr_end[r] = offset of the '\n' ending header r (or n);
+ *   d_seq_len[r] = bases of record r; d_out = the sequences of all records back to back in file order, with
+ *   '\n', '\r', ' ' and '\t' removed (record r starts at the exclusive prefix sum of d_seq_len); *d_n_out = their
+ *   total.  Bytes before the first header are ignored, as Biopython does.  upper != 0 maps a-z to A-Z on the fly
+ *   (the reference raises KeyError on lower case; soft-masked genomes need this).  d_bytes is MODIFIED (header lines
+ *   are blanked).  Temporary storage as in CUB: call with d_temp = NULL to get *temp_bytes. */
 int smg_fasta_index(const uint8_t* d_bytes, int64_t n, int64_t* d_hdr_start, uint64_t hdr_cap, uint64_t* d_n_hdr, void* stream);
 int smg_fasta_compact(uint8_t* d_bytes, int64_t n, const int64_t* d_hdr_start, int64_t n_hdr, int64_t* d_hdr_end,
                       uint64_t* d_seq_len, uint8_t* d_out, int64_t* d_n_out, int upper, void* d_temp, uint64_t* temp_bytes,

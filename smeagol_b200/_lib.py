@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SMEAGOL_B200_LIB", os.path.join(_HERE, "libsmeagol_b200.so"))  # env: tuning builds
 
 SMG_OK = 0
-CTR_HITS_APPENDED, CTR_NEAR, CTR_DEFINITE, CTR_ADJ_ACCEPTED, CTR_LAUNCHES, CTR_CANDIDATES = 0, 1, 2, 3, 4, 5
+CTR_HITS_APPENDED, CTR_NEAR, CTR_DEFINITE, CTR_ADJ_ACCEPTED, CTR_LAUNCHES, CTR_CANDIDATES, CTR_NEAR_TC = 0, 1, 2, 3, 4, 5, 6
 N_COUNTERS = 8
 MAX_REGTAB_WIDTH = 32
 ROW_DTYPE_FIELDS = [("word_off", "<i8"), ("g_off", "<i8"), ("g_len", "<i8"), ("n_avail", "<i4"), ("n_own", "<i4")]

@@ -43,12 +43,14 @@ static int fail(int code, const std::string& msg)
 struct Group {
     int wb;  // padded width
     int nm;  // PWMs per lane (1 or 2)
+    int tc;  // 1: every PWM of the group is on the tensor-core side of the split (decided by TRUE widths, not wb)
     int lane_motif[SMG_MAX_PWMS_PER_LANE][32];
     int64_t tab_off;
 };
 struct Bucket {
     int wb;
     int nm;
+    int tc;
     int first_group;
     int n_groups;
 };
@@ -481,7 +483,7 @@ __global__ void __launch_bounds__(256, SMG_FINALIZE_MIN_BLOCKS) finalize_candida
     n_acc = __reduce_add_sync(SMG_FULL_MASK, n_acc);
     if (lane == 0) {
         if (n_def) atomicAdd(&p.counters[SMG_CTR_DEFINITE], (unsigned long long)n_def);
-        if (n_near) atomicAdd(&p.counters[SMG_CTR_NEAR], (unsigned long long)n_near);
+        if (n_near) atomicAdd(&p.counters[SMG_CTR_NEAR_TC], (unsigned long long)n_near);
         if (n_acc) atomicAdd(&p.counters[SMG_CTR_ADJ_ACCEPTED], (unsigned long long)n_acc);
     }
 }
@@ -586,10 +588,14 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
             Group g;
             g.wb = std::max(wb, 2);
             g.nm = nm;
+            g.tc = 0;
             g.tab_off = 0;
             for (int m = 0; m < SMG_MAX_PWMS_PER_LANE; ++m)
                 for (int l = 0; l < 32; ++l) g.lane_motif[m][l] = -1;
             for (size_t i = 0; i < n_take; ++i) g.lane_motif[i / 32][i % 32] = pool[i];
+            // groups never mix the two sides (the pool is flushed at the split), so the first PWM decides; the padded
+            // width must not: width-1 PWMs are padded to wb = 2 and still belong to the register-table side of split 2
+            if (s->split > 0 && n_take > 0 && h_widths[pool[0]] >= s->split) g.tc = 1;
             pool.erase(pool.begin(), pool.begin() + n_take);
             s->groups.push_back(g);
         };
@@ -615,6 +621,7 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
     // buckets of equal (wb, nm), groups reordered so that a bucket is contiguous
     std::stable_sort(s->groups.begin(), s->groups.end(), [](const Group& a, const Group& b) {
         if (a.nm != b.nm) return a.nm > b.nm;
+        if (a.tc != b.tc) return a.tc < b.tc;
         return a.wb < b.wb;
     });
     std::vector<float> gtab;
@@ -622,8 +629,8 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
     std::vector<int32_t> lane_motif;
     for (size_t gi = 0; gi < s->groups.size(); ++gi) {
         Group& g = s->groups[gi];
-        if (s->buckets.empty() || s->buckets.back().wb != g.wb || s->buckets.back().nm != g.nm)
-            s->buckets.push_back({g.wb, g.nm, (int)gi, 0});
+        if (s->buckets.empty() || s->buckets.back().wb != g.wb || s->buckets.back().nm != g.nm || s->buckets.back().tc != g.tc)
+            s->buckets.push_back({g.wb, g.nm, g.tc, (int)gi, 0});
         s->buckets.back().n_groups++;
         g.tab_off = (int64_t)gtab.size();
         gtab_off.push_back(g.tab_off);
@@ -802,7 +809,7 @@ int smg_scan(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amask, 
     SMG_CUDA(cudaEventRecord(pool->fork, st));
     int bi = 0;
     for (const Bucket& b : s->buckets) {
-        if (s->split > 0 && b.wb >= s->split) continue;  // the tensor-core engine owns these (smg_scan_tc)
+        if (b.tc) continue;  // the tensor-core engine owns these (smg_scan_tc)
         smg_launch_fn fn = smg_get_launcher(b.wb, b.nm);
         if (!fn) return fail(SMG_ERR_INVALID, "smg_scan: no kernel for padded width " + std::to_string(b.wb));
         cudaStream_t bs = (bi == 0) ? st : pool->side[(bi - 1) % StreamPool::kSide];

@@ -388,7 +388,7 @@ class ScanPlan:
     def finish(self, sort=True):
         while True:
             c = self.counters.cpu().numpy()
-            n_app, n_near = int(c[_lib.CTR_HITS_APPENDED]), int(c[_lib.CTR_NEAR])
+            n_app, n_near = int(c[_lib.CTR_HITS_APPENDED]), int(c[_lib.CTR_NEAR])  # CTR_NEAR: entries of the `near` buffer only
             grow = False
             if n_near > self.near_cap:
                 self.near_cap = int(n_near * 1.25) + 1024
@@ -404,7 +404,7 @@ class ScanPlan:
             self._alloc()
             self.launch()
         n_hits = n_app if self.want_hits else 0
-        stats = {"n_definite": int(c[_lib.CTR_DEFINITE]), "n_near": n_near,
+        stats = {"n_definite": int(c[_lib.CTR_DEFINITE]), "n_near": n_near + int(c[_lib.CTR_NEAR_TC]),
                  "n_adjudicated_accepted": int(c[_lib.CTR_ADJ_ACCEPTED]),
                  "n_hits_total": int(c[_lib.CTR_DEFINITE]) + int(c[_lib.CTR_ADJ_ACCEPTED]), "chunk_len": self.chunk_len,
                  "n_chunks": self.n_chunks, "hit_cap": self.hit_cap, "near_cap": self.near_cap, "engine": self.engine,

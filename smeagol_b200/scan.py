@@ -68,6 +68,7 @@ def _melt_counts(table, row_labels, model, extra=None):
     one group; rows kept = PWMs with >=1 hit, columns kept = (id, name, sense) labels with >=1 hit; output iterates
     sorted columns (outer) x sorted (Matrix_id, width) (inner)."""
     ids, names, senses = row_labels
+    table = _collapse_motifs(table, model, 1)
     # rows of the encoding sharing (id, name, sense) collapse into one crosstab column; columns are sorted tuples
     keys = list(zip(ids, names, senses))
     col_uniques = sorted(set(keys))
@@ -96,6 +97,37 @@ def _melt_counts(table, row_labels, model, extra=None):
         "sense": _take([c[2] for c in col_uniques], rep),
         "num": sub.reshape(-1),
     })
+
+
+def _crosstab_rows(model):
+    """The crosstab's row index is (Matrix_id, width): PWMs sharing both collapse into ONE summed row (scan.py:137-140).
+    Returns (rep, inverse): rep[j] = first PWM of unique key j (keys in order of first appearance), inverse[m] = key of
+    PWM m; (None, None) when every key is unique (the usual case)."""
+    cached = getattr(model, "_crosstab_rows", None)
+    if cached is None:
+        seen, rep, inverse = {}, [], np.empty(model.channels, dtype=np.int64)
+        for m in range(model.channels):
+            k = (model.Matrix_ids[m], int(model.widths[m]))
+            if k not in seen:
+                seen[k] = len(rep)
+                rep.append(m)
+            inverse[m] = seen[k]
+        cached = (None, None) if len(rep) == model.channels else (np.array(rep, dtype=np.int64), inverse)
+        model._crosstab_rows = cached
+    return cached
+
+
+def _collapse_motifs(table, model, axis):
+    """Sum the PWM axis of a count table over PWMs with equal (Matrix_id, width); entries of the collapsed axis sit at
+    the index of the key's first PWM (the other duplicates become all-zero and drop out as unobserved rows)."""
+    rep, inverse = _crosstab_rows(model)
+    if rep is None:
+        return table
+    out = np.zeros_like(table)
+    idx = [slice(None)] * table.ndim
+    idx[axis] = rep[inverse]
+    np.add.at(out, tuple(idx), table)
+    return out
 
 
 def _motif_rank(model):
@@ -179,13 +211,16 @@ def _melt_binned(hist, row_labels, model, edges):
     zero-fills inside that rectangle, and melt walks sorted columns (outer) x sorted rows (inner); `bin` is the
     ordered categorical of pd.cut's right-closed intervals."""
     ids, names, senses = row_labels
+    hist = _collapse_motifs(hist, model, 1)
     keys = list(zip(ids, names, senses))
     col_uniques = sorted(set(keys))
     pos_of = {k: i for i, k in enumerate(col_uniques)}
     col_codes = np.fromiter((pos_of[k] for k in keys), dtype=np.int64, count=len(keys))
     agg = np.zeros((len(col_uniques),) + hist.shape[1:], dtype=np.int64)
     np.add.at(agg, col_codes, hist)
-    cats = pd.IntervalIndex.from_breaks(np.asarray(edges, dtype=np.float64), closed="right")
+    # the labels must be pd.cut's own (it rounds the breaks to 3 significant digits: (0.7, 0.8], not
+    # (0.7, 0.7999999999999999]) so that `bin` equals the reference's and the host route's column
+    cats = pd.cut(np.zeros(0), np.asarray(edges, dtype=np.float64)).categories
     cols = np.argwhere(agg.sum(axis=1) > 0)          # observed (label, bin) pairs, already in sorted order
     keep_m = np.flatnonzero(agg.sum(axis=(0, 2)) > 0)
     if cols.shape[0] == 0:

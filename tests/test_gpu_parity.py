@@ -477,7 +477,9 @@ def test_hybrid_engine_split_bit_identical():
     amb = "ACGTNWSMKRYBDHVZ"
     pa = np.array([0.23] * 4 + [0.08 / 12] * 12)
     seqs = [rand_seq(rng, 1500), rand_seq(rng, 777, amb, pa / pa.sum()), rand_seq(rng, 31), ""]
-    for split in (5, 10, 13, 22, 33):  # any width may be the split, also inside a K-depth class and above every PWM
+    # any width may be the split, also inside a K-depth class and above every PWM; split 2 has the width-1 PWMs (padded
+    # to width 2 in their lane group) on the register-table side -- they must not fall between the engines
+    for split in (2, 5, 10, 13, 22, 33):
         model = sb.models.PWMModel(df, tc_min_width=split)
         res, exp = check_against_oracle(model, seqs, 0.55, "both", chunk_len=256)
         assert res.stats["engine"] == "auto"

@@ -211,6 +211,64 @@ def test_melt_binned_equals_crosstab_of_hits():
         assert list(got["bin"].cat.categories) == list(want["bin"].cat.categories)
 
 
+def test_melt_routes_with_inexact_edges_and_duplicate_pwm_keys():
+    """(1) bin edges that are not exactly representable (np.arange(0.5, 1.0, 0.1), the reference's standard grid): the
+    dense route must carry pd.cut's own interval labels ((0.7, 0.8], not (0.7, 0.7999999999999999]); (2) PWMs sharing
+    (Matrix_id, width) collapse into one summed crosstab row in counts and binned counts (scan.py:137-140, :100-111)."""
+    import pandas as pd
+
+    from smeagol_b200 import scan as sscan
+
+    class M:
+        pass
+
+    rng = np.random.default_rng(11)
+    model = M()
+    model.channels = 6
+    model.Matrix_ids = np.array(["m0", "m1", "m0", "m2", "m1", "m0"], dtype=object)
+    model.widths = np.array([5, 7, 5, 9, 7, 6])                 # keys: (m0,5) x2, (m1,7) x2, (m2,9), (m0,6)
+    model.max_scores = rng.uniform(5, 12, size=6)
+
+    class E:
+        pass
+
+    enc = E()
+    enc.ids = np.array(["a", "b", "a", "c"], dtype=object)
+    enc.names = np.array(["a", "b", "a", "c"], dtype=object)
+    enc.senses = np.array(["+", "+", "-", "+"], dtype=object)
+    bins = np.arange(0.5, 1.0, 0.1)
+    edges = np.concatenate([bins, [1.0]])
+    n_hits = 300
+    seq_idx = rng.integers(0, 4, size=n_hits)
+    pwm_idx = rng.integers(0, 6, size=n_hits)
+    frac = rng.uniform(0.5001, 0.9999, size=n_hits)
+    scores = (frac * model.max_scores[pwm_idx]).astype(np.float32)
+    frac_used = scores / model.max_scores[pwm_idx]
+    hist = np.zeros((4, 6, len(bins)), dtype=np.int64)
+    b = np.searchsorted(edges, frac_used, side="left") - 1
+    ok = (frac_used > edges[0]) & (frac_used <= edges[-1])
+    np.add.at(hist, (seq_idx[ok], pwm_idx[ok], b[ok]), 1)
+    got = sscan._melt_binned(hist, (enc.ids, enc.names, enc.senses), model, edges)
+    want = sscan._bin_sites_by_score(enc, model, (seq_idx, np.zeros(n_hits, dtype=np.int64), pwm_idx), scores, bins)
+    assert got["bin"].cat.categories.equals(want["bin"].cat.categories)
+    assert "(0.7, 0.8]" in [str(c) for c in got["bin"].cat.categories]
+    assert len(got) == len(want)
+    for col in ("Matrix_id", "width", "id", "name", "sense", "num"):
+        assert list(got[col]) == list(want[col]), col
+    assert [str(x) for x in got["bin"]] == [str(x) for x in want["bin"]]
+    # counts: the reference's crosstab over the same hits
+    table = np.zeros((4, 6), dtype=np.int64)
+    np.add.at(table, (seq_idx, pwm_idx), 1)
+    gotc = sscan._melt_counts(table, (enc.ids, enc.names, enc.senses), model)
+    ct = pd.crosstab(index=[model.Matrix_ids[pwm_idx], model.widths[pwm_idx]],
+                     columns=[enc.ids[seq_idx], enc.names[seq_idx], enc.senses[seq_idx]])
+    wantc = ct.melt(ignore_index=False).reset_index()
+    wantc.columns = ["Matrix_id", "width", "id", "name", "sense", "num"]
+    assert len(gotc) == len(wantc) == 4 * 4                      # 4 distinct (Matrix_id, width) keys x 4 label columns
+    for col in wantc.columns:
+        assert list(gotc[col]) == list(wantc[col]), col
+
+
 def test_device_seq_behaves_like_a_seq():
     """seqrecord.DeviceSeq (sequences that live in a device ASCII buffer) keeps the Seq behaviour the reference API
     relies on; exercised here on a CPU tensor, the buffer type does not matter for the host-side logic."""
