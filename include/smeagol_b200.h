@@ -88,7 +88,8 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
                             smg_pwmset_t* out);
 int smg_pwmset_destroy(smg_pwmset_t set);
 /* info[0]=n_motifs info[1]=max_width info[2]=n_regtab_groups info[3]=n_buckets info[4]=n_wide_motifs
- * info[5]=sum over groups of padded width (dual groups count both strands) */
+ * info[5]=sum over groups of padded width (dual groups count both strands) info[6]=128-column blocks and
+ * info[7]=column groups of the tcgen05 prefilter */
 int smg_pwmset_info(smg_pwmset_t set, int64_t info[8]);
 
 /* encode.integer_encode (encode.py:47-68) on device.  d_src: concatenated ASCII bytes (input_kind 0) or integer
@@ -163,6 +164,18 @@ int smg_scan_tc(smg_pwmset_t set, const uint32_t* d_packed, const uint16_t* d_am
                 const float* d_thr_pre, const double* d_thr64, int pos_bits, int motif_bits, int cand_pos_bits,
                 uint64_t* d_cand, uint64_t cand_cap, uint64_t* d_hit_keys, float* d_hit_scores, uint64_t hit_cap,
                 int32_t* d_counts, uint64_t* d_counters, void* stream);
+
+/* Same contract, arguments and results as smg_scan_tc; the prefilter runs on the 5th-generation tensor cores instead:
+ * tcgen05.mma (kind::f16, fp32 accumulators in TMEM) with the fp16 tables of 128 (PWM, strand) columns resident in shared
+ * memory as the A operand and the soft one-hot of the sequence as a Toeplitz B operand (one 8-byte entry per base, the
+ * shared-memory descriptor overlaps its rows, no im2col matrix), 16 epilogue warps reading the accumulators back with
+ * tcgen05.ld and thresholding them (smeagol_b200/csrc/scan_tc5.cuh).  chunk_len should be a multiple of 512. */
+int smg_scan_tc5(smg_pwmset_t set, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
+                 const smg_row_t* d_rows, int32_t n_rows, const int32_t* d_out_rows, const smg_chunk_t* d_chunks,
+                 int32_t n_chunks, int32_t chunk_len, int strands, const float* d_thr_lo, const float* d_thr_hi,
+                 const float* d_thr_pre, const double* d_thr64, int pos_bits, int motif_bits, int cand_pos_bits,
+                 uint64_t* d_cand, uint64_t cand_cap, uint64_t* d_hit_keys, float* d_hit_scores, uint64_t hit_cap,
+                 int32_t* d_counts, uint64_t* d_counters, void* stream);
 
 /* fp64 adjudication of the near-threshold candidates: score64 = sum of the fp32 operands in double, hit iff
  * score64 > d_thr64[motif] (thr = frac * max_scores computed on the host as models.py:141 does). */

@@ -18,7 +18,7 @@ NEAR_BYTES = 24
 # every symbol include/smeagol_b200.h declares (tests/test_cabi.py checks the export list against the header)
 EXPORTS = [
     "smg_version", "smg_last_error", "smg_launch_count", "smg_pwmset_create", "smg_pwmset_create_split", "smg_pwmset_destroy", "smg_pwmset_info",
-    "smg_pack", "smg_scan", "smg_scan_tc", "smg_adjudicate", "smg_sort_hits", "smg_predict_dense", "smg_variant_sites",
+    "smg_pack", "smg_scan", "smg_scan_tc", "smg_scan_tc5", "smg_adjudicate", "smg_sort_hits", "smg_predict_dense", "smg_variant_sites",
     "smg_variant_windows", "smg_fasta_index", "smg_fasta_compact", "smg_kmer_shuffle", "smg_bin_hits",
 ]
 
@@ -53,6 +53,7 @@ def load():
                              vp, vp, u64, vp, u64, vp, vp, vp]
     lib.smg_scan_tc.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int,
                                 ctypes.c_int, ctypes.c_int, vp, u64, vp, vp, u64, vp, vp, vp]
+    lib.smg_scan_tc5.argtypes = lib.smg_scan_tc.argtypes
     lib.smg_bin_hits.argtypes = [vp, vp, u64, ctypes.c_int, ctypes.c_int, vp, vp, i32, i32, vp, vp]
     lib.smg_kmer_shuffle.argtypes = [vp, i64, vp, vp, i32, i32, u64, vp, vp, i64, vp]
     lib.smg_fasta_index.argtypes = [vp, i64, vp, u64, vp, vp]

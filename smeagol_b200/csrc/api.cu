@@ -17,6 +17,8 @@
 #include "hmma_launchers.h"
 #include <cuda_fp16.h>
 #include "variant_launchers.h"
+#include "scan_tc5_params.cuh"
+#include "tc5_launchers.h"
 
 // ------------------------------------------------------------------------------------------ host-side state
 static thread_local std::string g_err;
@@ -74,6 +76,16 @@ struct smg_pwmset {
     float* d_thr_pre_col = nullptr;
     int32_t* d_dual_list = nullptr;
     int32_t* d_nondual_list = nullptr;
+    // tcgen05 prefilter (scan_tc5.cuh): 128-column blocks of (PWM, strand) columns grouped into column groups whose fp16
+    // images fit in one CTA's shared memory
+    int t5_n_blocks = 0, t5_n_groups = 0, t5_max_image = 0;
+    uint8_t* d_t5_img = nullptr;
+    int64_t* d_t5_cg_img_off = nullptr;
+    int32_t* d_t5_cg_first_blk = nullptr;
+    int32_t* d_t5_blk_ks = nullptr;
+    int32_t* d_t5_blk_off = nullptr;
+    int32_t* d_t5_col_id = nullptr;
+    float* d_t5_thr_pre_col = nullptr;
     int64_t sum_padded = 0;
     float* d_nat = nullptr;
     int32_t* d_width = nullptr;
@@ -720,6 +732,75 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
         }
         s->n_hcols = (int64_t)col_id.size();
     }
+    // ---- tcgen05 prefilter tables: columns sorted by K depth, 128 per block; a block's image is its fp16 weights as the
+    // K-major A operand of tcgen05.mma without swizzle: element (column m, k) at (k / 8) * 2048 + m * 16 + (k % 8) * 2,
+    // k = 4 * PWM row + base; blocks are packed into column groups of at most smg_tc5_max_image_bytes()
+    std::vector<uint8_t> t5_img;
+    std::vector<int64_t> t5_cg_img_off;
+    std::vector<int32_t> t5_cg_first_blk, t5_blk_ks, t5_blk_off, t5_col_id;
+    {
+        std::vector<int> cols;  // motif * 2 + strand, ascending K depth
+        for (int ks = 1; ks <= SMG_MAX_REGTAB_WIDTH / 4; ++ks)
+            for (int m = 0; m < n_motifs; ++m)
+                if ((h_widths[m] + 3) / 4 == ks && (s->split == 0 || h_widths[m] >= s->split)) {
+                    cols.push_back(m * 2);
+                    cols.push_back(m * 2 + 1);
+                }
+        const int n_blocks = (int)((cols.size() + 127) / 128);
+        std::vector<int> bks(n_blocks, 1);
+        int units = 0;
+        for (int b = 0; b < n_blocks; ++b) {
+            const size_t last = std::min(cols.size(), (size_t)(b + 1) * 128) - 1;
+            bks[b] = (h_widths[cols[last] >> 1] + 3) / 4;  // sorted by K depth: the last column is the deepest
+            units += bks[b];
+        }
+        const int cap_units = std::min(smg_tc5_max_image_bytes() / smg::kTc5UnitBytes, 1 << 20);
+        const int n_groups = n_blocks ? std::max((units + cap_units - 1) / cap_units, (n_blocks + smg_tc5_max_blocks() - 1) / smg_tc5_max_blocks()) : 0;
+        auto h16 = [](float v) {
+            if (v == v && v > 60000.f && v < 3.0e38f) v = 60000.f;   // finite weights stay finite in fp16
+            if (v == v && v < -60000.f && v > -3.0e38f) v = -60000.f;
+            return __half_as_ushort(__float2half_rn(v));
+        };
+        int b = 0;
+        for (int g = 0; g < n_groups; ++g) {
+            // even split of the remaining units over the remaining groups, never above the capacity
+            int rem_units = 0;
+            for (int q = b; q < n_blocks; ++q) rem_units += bks[q];
+            const int target = (rem_units + (n_groups - g) - 1) / (n_groups - g);
+            t5_cg_first_blk.push_back(b);
+            t5_cg_img_off.push_back((int64_t)t5_img.size());
+            int used = 0, nb = 0;
+            while (b < n_blocks && nb < smg_tc5_max_blocks() && used + bks[b] <= cap_units && (used < target || g == n_groups - 1)) {
+                const int ks = bks[b];
+                t5_blk_ks.push_back(ks);
+                t5_blk_off.push_back(used * smg::kTc5UnitBytes);
+                const size_t base = t5_img.size();
+                t5_img.resize(base + (size_t)ks * smg::kTc5UnitBytes, 0);
+                for (int mrow = 0; mrow < 128; ++mrow) {
+                    const size_t ci = (size_t)b * 128 + mrow;
+                    const int cid = ci < cols.size() ? cols[ci] : -1;
+                    t5_col_id.push_back(cid);
+                    if (cid < 0) continue;
+                    const int m = cid >> 1, st = cid & 1, wm = h_widths[m];
+                    const float* T = h_weights + s->offs[m] * 4;
+                    for (int k = 0; k < 4 * wm; ++k) {
+                        const int row = k >> 2, bb = k & 3;
+                        const float v = st ? T[(wm - 1 - row) * 4 + (3 - bb)] : T[row * 4 + bb];
+                        const uint16_t hv = h16(v);
+                        memcpy(&t5_img[base + (size_t)(k / 8) * 2048 + (size_t)mrow * 16 + (size_t)(k % 8) * 2], &hv, 2);
+                    }
+                }
+                used += ks;
+                ++nb;
+                ++b;
+            }
+            s->t5_max_image = std::max(s->t5_max_image, used * smg::kTc5UnitBytes);
+        }
+        if (b != n_blocks) { delete s; return fail(SMG_ERR_INVALID, "smg_pwmset_create: tcgen05 column groups do not cover the library"); }
+        t5_cg_first_blk.push_back(n_blocks);
+        s->t5_n_blocks = n_blocks;
+        s->t5_n_groups = n_groups;
+    }
     std::vector<float> nat(h_weights, h_weights + tot * 4);
     std::vector<int32_t> wv(h_widths, h_widths + n_motifs);
     std::vector<int32_t> widev(s->wide.begin(), s->wide.end());
@@ -730,6 +811,10 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
         (rc = upload(&s->d_lane_motif, lane_motif)) ||
         (rc = upload(&s->d_afrag, afrag)) || (rc = upload(&s->d_cg_afrag_off, cg_off)) || (rc = upload(&s->d_col_id, col_id)) ||
         (rc = upload(&s->d_thr_pre_col, std::vector<float>((size_t)std::max<int64_t>(s->n_hcols, 1), 0.f))) ||
+        (rc = upload(&s->d_t5_img, t5_img)) || (rc = upload(&s->d_t5_cg_img_off, t5_cg_img_off)) ||
+        (rc = upload(&s->d_t5_cg_first_blk, t5_cg_first_blk)) || (rc = upload(&s->d_t5_blk_ks, t5_blk_ks)) ||
+        (rc = upload(&s->d_t5_blk_off, t5_blk_off)) || (rc = upload(&s->d_t5_col_id, t5_col_id)) ||
+        (rc = upload(&s->d_t5_thr_pre_col, std::vector<float>((size_t)std::max(s->t5_n_blocks * 128, 1), 0.f))) ||
         (rc = upload(&s->d_wide, widev)) || (rc = upload(&s->d_dual_list, dualv)) || (rc = upload(&s->d_nondual_list, nondualv))) {
         smg_pwmset_destroy(s);
         return rc;
@@ -742,6 +827,8 @@ int smg_pwmset_destroy(smg_pwmset_t s)
 {
     if (!s) return SMG_OK;
     cudaFree(s->d_nat); cudaFree(s->d_width); cudaFree(s->d_off); cudaFree(s->d_gtab); cudaFree(s->d_gtab_off);
+    cudaFree(s->d_t5_img); cudaFree(s->d_t5_cg_img_off); cudaFree(s->d_t5_cg_first_blk); cudaFree(s->d_t5_blk_ks);
+    cudaFree(s->d_t5_blk_off); cudaFree(s->d_t5_col_id); cudaFree(s->d_t5_thr_pre_col);
     cudaFree(s->d_lane_motif); cudaFree(s->d_afrag); cudaFree(s->d_cg_afrag_off); cudaFree(s->d_col_id); cudaFree(s->d_thr_pre_col); cudaFree(s->d_wide); cudaFree(s->d_dual_list); cudaFree(s->d_nondual_list);
     delete s;
     return SMG_OK;
@@ -752,7 +839,7 @@ int smg_pwmset_info(smg_pwmset_t s, int64_t info[8])
     if (!s || !info) return fail(SMG_ERR_INVALID, "smg_pwmset_info: bad argument");
     memset(info, 0, 8 * sizeof(int64_t));
     info[0] = s->n_motifs; info[1] = s->max_w; info[2] = (int64_t)s->groups.size(); info[3] = (int64_t)s->buckets.size();
-    info[4] = (int64_t)s->wide.size(); info[5] = s->sum_padded;
+    info[4] = (int64_t)s->wide.size(); info[5] = s->sum_padded; info[6] = s->t5_n_blocks; info[7] = s->t5_n_groups;
     return SMG_OK;
 }
 
@@ -890,6 +977,54 @@ int smg_scan_tc(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amas
     }
     // PWMs wider than the register / fragment kernels: emitted as candidates by a generic kernel? No -- scored directly.
     if (!s->wide.empty() && s->split == 0) return fail(SMG_ERR_UNSUPPORTED, "smg_scan_tc: PWMs wider than 32 need smg_scan");
+    finalize_candidates_kernel<<<148 * SMG_FINALIZE_MIN_BLOCKS * 2, 256, 0, st>>>(p, reinterpret_cast<const unsigned long long*>(d_cand), cand_cap,
+                                                       hp.cand_shift, d_thr64);
+    SMG_LAUNCH_CHECK("finalize_candidates_kernel");
+    return SMG_OK;
+}
+
+int smg_scan_tc5(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes, const smg_row_t* d_rows,
+                 int32_t n_rows, const int32_t* d_out_rows, const smg_chunk_t* d_chunks, int32_t n_chunks, int32_t chunk_len,
+                 int strands, const float* d_thr_lo, const float* d_thr_hi, const float* d_thr_pre, const double* d_thr64,
+                 int pos_bits, int motif_bits, int cand_pos_bits, uint64_t* d_cand, uint64_t cand_cap, uint64_t* d_hit_keys,
+                 float* d_hit_scores, uint64_t hit_cap, int32_t* d_counts, uint64_t* d_counters, void* stream)
+{
+    if (!s || !d_packed || !d_amask || !d_rows || n_rows <= 0 || !d_out_rows || !d_chunks || n_chunks < 0 || !d_thr_lo ||
+        !d_thr_hi || !d_thr_pre || !d_thr64 || !d_counters || !d_cand || cand_cap == 0)
+        return fail(SMG_ERR_INVALID, "smg_scan_tc5: bad argument");
+    if (chunk_len <= 0 || (chunk_len & 15)) return fail(SMG_ERR_INVALID, "smg_scan_tc5: chunk_len must be a positive multiple of 16");
+    if ((strands & 3) == 0 || (strands & ~3)) return fail(SMG_ERR_INVALID, "smg_scan_tc5: strands must be 1, 2 or 3");
+    if (pos_bits <= 0 || motif_bits <= 0 || pos_bits + motif_bits > 63) return fail(SMG_ERR_INVALID, "smg_scan_tc5: bad key layout");
+    if ((1ll << motif_bits) < s->n_motifs) return fail(SMG_ERR_INVALID, "smg_scan_tc5: motif_bits too small");
+    if (cand_pos_bits <= 0 || cand_pos_bits + motif_bits + 1 > 62) return fail(SMG_ERR_INVALID, "smg_scan_tc5: bad candidate layout");
+    if ((d_hit_keys == nullptr) != (d_hit_scores == nullptr)) return fail(SMG_ERR_INVALID, "smg_scan_tc5: hit buffers must both be set or NULL");
+    if (!s->wide.empty() && s->split == 0) return fail(SMG_ERR_UNSUPPORTED, "smg_scan_tc5: PWMs wider than 32 need smg_scan");
+    if (n_chunks == 0 || s->t5_n_blocks == 0) return SMG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    ScanParams p;
+    fill_params(p, s, d_packed, d_amask, d_codes, d_rows, d_out_rows);
+    p.chunks = d_chunks; p.chunk_len = chunk_len; p.strands = strands; p.thr_lo = d_thr_lo; p.thr_hi = d_thr_hi;
+    p.pos_bits = pos_bits; p.motif_bits = motif_bits;
+    p.hit_keys = reinterpret_cast<unsigned long long*>(d_hit_keys); p.hit_scores = d_hit_scores; p.hit_cap = hit_cap;
+    p.counts = d_counts; p.counters = reinterpret_cast<unsigned long long*>(d_counters);
+    const int64_t n_cols = (int64_t)s->t5_n_blocks * 128;
+    hmma_thr_kernel<<<(unsigned)((n_cols + 255) / 256), 256, 0, st>>>(s->d_t5_col_id, d_thr_pre, strands, n_cols, s->d_t5_thr_pre_col);
+    SMG_LAUNCH_CHECK("hmma_thr_kernel");
+    smg::Tc5Params hp;
+    hp.sp = p; hp.wimg = s->d_t5_img; hp.cg_img_off = s->d_t5_cg_img_off; hp.cg_first_blk = s->d_t5_cg_first_blk;
+    hp.blk_ks = s->d_t5_blk_ks; hp.blk_off = s->d_t5_blk_off; hp.thr_pre_col = s->d_t5_thr_pre_col; hp.col_id = s->d_t5_col_id;
+    hp.n_chunks = n_chunks; hp.cand_shift = cand_pos_bits + motif_bits + 1;
+    hp.cand = reinterpret_cast<unsigned long long*>(d_cand); hp.cand_cap = cand_cap;
+    int n_sm = 148;
+    {
+        int dev = 0;
+        SMG_CUDA(cudaGetDevice(&dev));
+        SMG_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int grid_x = std::max(1, std::min(n_chunks, n_sm / s->t5_n_groups));
+    cudaError_t e = smg_launch_tc5(hp, grid_x, s->t5_n_groups, s->t5_max_image, st);
+    if (e != cudaSuccess) return fail(SMG_ERR_CUDA, std::string("scan_tc5_kernel: ") + cudaGetErrorString(e));
+    ++g_launches;
     finalize_candidates_kernel<<<148 * SMG_FINALIZE_MIN_BLOCKS * 2, 256, 0, st>>>(p, reinterpret_cast<const unsigned long long*>(d_cand), cand_cap,
                                                        hp.cand_shift, d_thr64);
     SMG_LAUNCH_CHECK("finalize_candidates_kernel");

@@ -19,6 +19,7 @@ ROW_PAD_BASES = 96  # every row is followed by at least this many 'Z' bases (hal
 NEAR_REL = 1e-5     # half-width of the near-threshold band, relative to sum_k max_b |T[k,b]|
 STRANDS = {"none": 1, "only": 2, "both": 3}
 DEFAULT_ENGINE = "regtab"
+DEFAULT_TC_KIND = "hmma"  # tensor-core prefilter of the 'auto' / tensor-core engines: 'hmma' (mma.sync) or 'tc5' (tcgen05 + TMEM)
 DEFAULT_TC_MIN_WIDTH = 7  # measured per width (profiles/r01_bench_widths.txt): the register-table engine wins up to W = 6 (hit density >= 6e-3 at thr 0.7), the tensor-core prefilter from W = 7
 
 
@@ -274,6 +275,9 @@ class ScanPlan:
         same results).  Default: $SMEAGOL_B200_ENGINE or DEFAULT_ENGINE."""
         self.lib = _lib.load()
         self.engine = engine or os.environ.get("SMEAGOL_B200_ENGINE", DEFAULT_ENGINE)
+        self.tc_kind = os.environ.get("SMEAGOL_B200_TC_KIND", DEFAULT_TC_KIND)
+        if self.engine == "tc5":
+            self.engine, self.tc_kind = "hmma", "tc5"
         if pwmset.tc_min_width > 0:
             self.engine = "auto"    # the PWM set was built split: both engines run, each on its side
         elif self.engine == "auto" or (self.engine == "hmma" and pwmset.n_wide > 0):
@@ -298,6 +302,8 @@ class ScanPlan:
                              % (n_out_rows, batch.max_g_len, M))
         self.chunk_len = (pick_chunk_len(batch.total_own, pwmset.n_groups, n_rows=batch.n_rows) if chunk_len is None
                           else int(chunk_len))
+        if chunk_len is None and self.engine in ("hmma", "auto") and self.tc_kind == "tc5":
+            self.chunk_len = max(512, (self.chunk_len + 511) // 512 * 512)  # the tcgen05 prefilter works in tiles of 512 starts
         chunks = batch.chunks(self.chunk_len)
         self.n_chunks = len(chunks)
         self.d_chunks = _to_dev(chunks, dev) if len(chunks) else torch.zeros(8, dtype=torch.uint8, device=dev)
@@ -363,12 +369,13 @@ class ScanPlan:
     def launch_tc_side(self):
         """Tensor-core prefilter + exact second pass on its side of the width split."""
         b, lib = self.batch, self.lib
-        _lib.check(lib.smg_scan_tc(self.pwmset.handle, _ptr(b.packed), _ptr(b.amask), _ptr(b.codes), _ptr(b.d_rows), b.n_rows,
+        fn = lib.smg_scan_tc5 if self.tc_kind == "tc5" else lib.smg_scan_tc
+        _lib.check(fn(self.pwmset.handle, _ptr(b.packed), _ptr(b.amask), _ptr(b.codes), _ptr(b.d_rows), b.n_rows,
                                    _ptr(self.d_out_rows), _ptr(self.d_chunks), self.n_chunks, self.chunk_len, self.strands,
                                    _ptr(self.d_lo), _ptr(self.d_hi), _ptr(self.d_pre), _ptr(self.d_thr), self.pos_bits,
                                    self.motif_bits, self.cand_pos_bits, _ptr(self.cand), self.cand_cap, _ptr(self.keys),
                                    _ptr(self.scores), self.hit_cap, _ptr(self.counts), _ptr(self.counters), _stream()),
-                   "smg_scan_tc")
+                   "smg_scan_tc5" if self.tc_kind == "tc5" else "smg_scan_tc")
 
     def _launch_regtab(self):
         b, lib = self.batch, self.lib
@@ -408,6 +415,7 @@ class ScanPlan:
                  "n_adjudicated_accepted": int(c[_lib.CTR_ADJ_ACCEPTED]),
                  "n_hits_total": int(c[_lib.CTR_DEFINITE]) + int(c[_lib.CTR_ADJ_ACCEPTED]), "chunk_len": self.chunk_len,
                  "n_chunks": self.n_chunks, "hit_cap": self.hit_cap, "near_cap": self.near_cap, "engine": self.engine,
+                 "tc_kind": self.tc_kind if self.engine in ("hmma", "auto") else None,
                  "n_candidates": int(c[_lib.CTR_CANDIDATES])}
         keys, scores = self.keys, self.scores
         if self.want_hits and sort and n_hits > 0:

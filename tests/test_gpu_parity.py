@@ -432,16 +432,17 @@ def test_edge_inputs():
         sb.scan.scan_sequences(recs, model, 1.5)
 
 
-@pytest.fixture
-def hmma_engine():
+@pytest.fixture(params=["hmma", "tc5"])
+def hmma_engine(request):
+    """'hmma': warp-level mma.sync prefilter (scan_hmma.cuh); 'tc5': tcgen05.mma + TMEM prefilter (scan_tc5.cuh)."""
     global ENGINE
-    ENGINE = "hmma"
-    yield
+    ENGINE = request.param
+    yield request.param
     ENGINE = None
 
 
 def test_tensor_core_engine_bit_identical(hmma_engine):
-    """The tensor-core prefilter + exact second pass must give the same hits, fp32 scores and counts as the oracle
+    """The tensor-core prefilters + exact second pass must give the same hits, fp32 scores and counts as the oracle
     (and hence as the register-table engine): widths 1..32, IUPAC codes, every rcomp mode, chunk boundaries."""
     sb = _sb()
     rng = np.random.default_rng(41)
@@ -455,13 +456,20 @@ def test_tensor_core_engine_bit_identical(hmma_engine):
     pa = np.array([0.23] * 4 + [0.08 / 12] * 12)
     seqs = [rand_seq(rng, 1500), rand_seq(rng, 777, amb, pa / pa.sum()), rand_seq(rng, 31), "ACGTA", ""]
     res, exp = check_against_oracle(model, seqs, 0.55, "both", chunk_len=256)
-    assert res.stats["engine"] == "hmma" and res.stats["n_candidates"] >= len(exp["row"])
+    assert res.stats["engine"] == "hmma" and res.stats["tc_kind"] == hmma_engine
+    assert res.stats["n_candidates"] >= len(exp["row"])
     check_against_oracle(model, seqs, 0.55, "none", chunk_len=4096)
     check_against_oracle(model, seqs, 0.55, "only", chunk_len=256)
     model2 = sb.models.PWMModel(synth_pwms(rng, 150, 5, 24), tc_min_width=0)
     check_against_oracle(model2, [rand_seq(rng, 3000), "N" * 300 + rand_seq(rng, 500) + "N" * 100], 0.6, "both", chunk_len=512)
     check_against_oracle(model2, [rand_seq(rng, 900)], 1.0, "both")
     check_against_oracle(model2, [rand_seq(rng, 900)], 0.2, "both", atol=1e-5)
+    # many tiles per CTA, several column blocks and column groups, rows that end inside a tile, default chunking
+    model3 = sb.models.PWMModel(synth_pwms(rng, 700, 6, 24), tc_min_width=0)
+    long_seqs = [rand_seq(rng, 40000), rand_seq(rng, 5000, "ACGTN", [0.24, 0.24, 0.24, 0.24, 0.04]), rand_seq(rng, 513),
+                 rand_seq(rng, 511), rand_seq(rng, 1024)]
+    res3, exp3 = check_against_oracle(model3, long_seqs, 0.7, "both")
+    assert len(exp3["row"]) > 10000
 
 
 def test_hybrid_engine_split_bit_identical():
