@@ -440,6 +440,7 @@ __global__ void __launch_bounds__(256, SMG_FINALIZE_MIN_BLOCKS) finalize_candida
         unsigned long long key = 0;
         if (i < n_cand) {
             const unsigned long long c = cand[i];
+            if (c != SMG_CAND_INVALID) {  // padding of a block reserved by the tcgen05 prefilter's consumer warps
             const int st = (int)(c & 1ull);
             const int motif = (int)((c >> 1) & ((1ull << p.motif_bits) - 1ull));
             const long long s = (long long)((c >> (p.motif_bits + 1)) & ((1ull << (cand_shift - p.motif_bits - 1)) - 1ull));
@@ -467,6 +468,7 @@ __global__ void __launch_bounds__(256, SMG_FINALIZE_MIN_BLOCKS) finalize_candida
                     key = ((unsigned long long)(unsigned)p.out_rows[r * 2 + st] << key_shift) |
                           ((unsigned long long)pos << p.motif_bits) | (unsigned long long)(unsigned)motif;
                 }
+            }
             }
         }
         if (p.hit_keys) {
@@ -734,7 +736,7 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
     }
     // ---- tcgen05 prefilter tables: columns sorted by K depth, 128 per block; a block's image is its fp16 weights as the
     // K-major A operand of tcgen05.mma without swizzle: element (column m, k) at (k / 8) * 2048 + m * 16 + (k % 8) * 2,
-    // k = 4 * PWM row + base; blocks are packed into column groups of at most smg_tc5_max_image_bytes()
+    // k = 4 * PWM row + base; blocks are dealt into column groups of at most smg_tc5_max_image_bytes()
     std::vector<uint8_t> t5_img;
     std::vector<int64_t> t5_cg_img_off;
     std::vector<int32_t> t5_cg_first_blk, t5_blk_ks, t5_blk_off, t5_col_id;
@@ -755,22 +757,32 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
             units += bks[b];
         }
         const int cap_units = std::min(smg_tc5_max_image_bytes() / smg::kTc5UnitBytes, 1 << 20);
-        const int n_groups = n_blocks ? std::max((units + cap_units - 1) / cap_units, (n_blocks + smg_tc5_max_blocks() - 1) / smg_tc5_max_blocks()) : 0;
+        // Column groups: block i goes to group i % G (dealt round-robin, so every group gets the same mix of K depths and
+        // hit densities and the CTAs of all groups finish together); G = the smallest count for which every group fits
+        auto deal_ok = [&](int G) {
+            for (int g = 0; g < G; ++g) {
+                int used = 0, nb = 0;
+                for (int q = g; q < n_blocks; q += G) { used += bks[q]; ++nb; }
+                if (used > cap_units || nb > smg_tc5_max_blocks()) return false;
+            }
+            return true;
+        };
+        int n_groups = 0;
+        if (n_blocks) {
+            n_groups = std::max(1, (units + cap_units - 1) / cap_units);
+            while (n_groups < n_blocks && !deal_ok(n_groups)) ++n_groups;
+        }
         auto h16 = [](float v) {
             if (v == v && v > 60000.f && v < 3.0e38f) v = 60000.f;   // finite weights stay finite in fp16
             if (v == v && v < -60000.f && v > -3.0e38f) v = -60000.f;
             return __half_as_ushort(__float2half_rn(v));
         };
-        int b = 0;
+        int emitted = 0;
         for (int g = 0; g < n_groups; ++g) {
-            // even split of the remaining units over the remaining groups, never above the capacity
-            int rem_units = 0;
-            for (int q = b; q < n_blocks; ++q) rem_units += bks[q];
-            const int target = (rem_units + (n_groups - g) - 1) / (n_groups - g);
-            t5_cg_first_blk.push_back(b);
+            t5_cg_first_blk.push_back(emitted);
             t5_cg_img_off.push_back((int64_t)t5_img.size());
-            int used = 0, nb = 0;
-            while (b < n_blocks && nb < smg_tc5_max_blocks() && used + bks[b] <= cap_units && (used < target || g == n_groups - 1)) {
+            int used = 0;
+            for (int b = g; b < n_blocks; b += n_groups) {
                 const int ks = bks[b];
                 t5_blk_ks.push_back(ks);
                 t5_blk_off.push_back(used * smg::kTc5UnitBytes);
@@ -791,12 +803,14 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
                     }
                 }
                 used += ks;
-                ++nb;
-                ++b;
+                ++emitted;
             }
             s->t5_max_image = std::max(s->t5_max_image, used * smg::kTc5UnitBytes);
         }
-        if (b != n_blocks) { delete s; return fail(SMG_ERR_INVALID, "smg_pwmset_create: tcgen05 column groups do not cover the library"); }
+        if (n_blocks && (emitted != n_blocks || !deal_ok(n_groups))) {
+            delete s;
+            return fail(SMG_ERR_INVALID, "smg_pwmset_create: tcgen05 column groups do not cover the library");
+        }
         t5_cg_first_blk.push_back(n_blocks);
         s->t5_n_blocks = n_blocks;
         s->t5_n_groups = n_groups;

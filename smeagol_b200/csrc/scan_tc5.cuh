@@ -18,8 +18,14 @@
 //   * D lives in TMEM (2 x 256 columns, double buffered): the MMA of the next accumulator runs while 16 epilogue warps
 //     read the current one (tcgen05.ld 32x32b.x64: thread = one (PWM, strand) column, 64 window starts in registers),
 //     release the buffer, reduce with 3-input max and compare with the thread's prefilter threshold.  Groups of 16
-//     cells that hold a candidate are appended whole to a per-warp queue in shared memory (ballot + prefix popcount);
-//     the queues are drained per chunk into 64-bit candidates (row, start, motif, strand) with one atomic per flush.
+//     cells that hold a candidate are TRANSPOSED through a small per-warp scratch in shared memory: the flagged lanes
+//     store their 16 cells, then the warp re-reads them with lane = cell (two flagged lanes per ballot) and writes the
+//     survivors as 64-bit candidates (row, start, motif, strand) straight into the global list, in blocks of 128 slots
+//     that the warp reserves one block AHEAD (the atomic's latency never stalls it; the unused tail of the last blocks
+//     is padded with an invalid marker that the exact pass skips).  The epilogue warps synchronise on every
+//     accumulator, so their per-step work must be short and even: a version that queued the groups and drained the
+//     queue every few steps ran 3.3x slower at hit density 1.5e-3 (one draining warp stalls all 16), and two
+//     asynchronous consumer warps could not keep up (a single warp's dependent chain: 275 cycles per pair of groups).
 //
 // Warp roles (576 threads, 1 CTA per SM, persistent over chunks): warp 0 = strip producer, warp 1 = MMA issuer (one
 // elected lane), warps 2..17 = epilogue.  Synchronisation is mbarrier-only: xfull/xempty (strips), tfull/tempty (TMEM).
@@ -106,73 +112,6 @@ __device__ __forceinline__ void tc5_build_strips(const ScanParams& p, const smg_
             }
         }
     }
-}
-
-// ---- epilogue: drain of one warp's queue.  Entry j = 16 accumulator cells of one column (tag: source lane, group,
-// parity, block, tile); every lane takes one entry, compares its 16 cells with the column's threshold and the warp
-// compacts the survivors into its stage (ballot + prefix popcount), flushed to the global list with one atomic.
-struct Tc5Drain {
-    const Tc5Params* hp;
-    const float* qv;                 // [kTc5QCap][16]
-    const uint32_t* qt;              // [kTc5QCap]
-    unsigned long long* stage;       // [kTc5Stage]
-    int first_blk, quad, colchunk;
-};
-
-static __device__ __noinline__ int tc5_flush(const Tc5Params& hp, const unsigned long long* stage, const int nst, const int lane)
-{
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&hp.sp.counters[SMG_CTR_CANDIDATES], (unsigned long long)nst);
-    base = __shfl_sync(SMG_FULL_MASK, base, 0);
-    for (int k = lane; k < nst; k += 32)
-        if (base + k < hp.cand_cap) hp.cand[base + k] = stage[k];
-    __syncwarp();
-    return 0;
-}
-
-static __device__ __noinline__ int tc5_drain(const Tc5Drain& d, const int cnt, int nst, const int c0, const int c1,
-                                             const unsigned long long rowbits, const int lane)
-{
-    const Tc5Params& hp = *d.hp;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const int pos_shift = hp.sp.motif_bits + 1;
-    for (int j0 = 0; j0 < cnt; j0 += 32) {
-        const int j = j0 + lane;
-        const bool have = j < cnt;
-        const uint32_t tag = have ? d.qt[j] : 0u;
-        const int srclane = (int)(tag & 31u), g = (int)((tag >> 5) & 3u), e = (int)((tag >> 7) & 1u);
-        const int blk = (int)((tag >> 8) & 63u), tile = (int)(tag >> 14);
-        const int col = (d.first_blk + blk) * 128 + d.quad * 32 + srclane;
-        const float thr = have ? hp.thr_pre_col[col] : __int_as_float(0x7f800000);
-        const int cid = have ? hp.col_id[col] : -1;
-        const int s0 = c0 + tile * kTc5Tile + 2 * (d.colchunk * 64 + g * 16) + e;  // window start of cell 0
-        float v[16];
-        if (have) {
-            const float4* src = reinterpret_cast<const float4*>(d.qv + j * 16);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 t = src[q];
-                v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int s = s0 + 2 * i;
-            const bool is = (v[i] > thr) && (s < c1);
-            const unsigned m = __ballot_sync(SMG_FULL_MASK, is);
-            if (m) {
-                if (is) d.stage[nst + __popc(m & lt_mask)] = rowbits | ((unsigned long long)(unsigned)s << pos_shift) |
-                                                             (unsigned long long)(unsigned)cid;
-                nst += __popc(m);
-                __syncwarp();
-                if (nst > kTc5Stage - 32) nst = tc5_flush(hp, d.stage, nst, lane);
-            }
-        }
-    }
-    return nst;
 }
 
 __global__ void __launch_bounds__(kTc5Threads, 1) scan_tc5_kernel(const __grid_constant__ Tc5Params hp)
@@ -281,29 +220,34 @@ __global__ void __launch_bounds__(kTc5Threads, 1) scan_tc5_kernel(const __grid_c
         const int ew = warp - 2;
         const int quad = warp & 3;      // TMEM lanes 32 * (warp % 4) .. + 31 are the ones this warp may read
         const int colchunk = ew >> 2;   // 64 of the accumulator's 256 columns (window starts)
-        float* qv = reinterpret_cast<float*>(smem + kTc5OffQV) + ew * kTc5QCap * 16;
-        uint32_t* qt = reinterpret_cast<uint32_t*>(smem + kTc5OffQT) + ew * kTc5QCap;
-        unsigned long long* stage = reinterpret_cast<unsigned long long*>(smem + kTc5OffStage) + ew * kTc5Stage;
-        Tc5Drain dr;
-        dr.hp = &hp; dr.qv = qv; dr.qt = qt; dr.stage = stage; dr.first_blk = first_blk; dr.quad = quad; dr.colchunk = colchunk;
+        uint8_t* scratch = smem + kTc5OffScratch + ew * kTc5ScratchBytes;
         const unsigned lt_mask = (1u << lane) - 1u;
+        const int cell = lane & 15, sub = lane >> 4;
+        const int pos_shift = p.motif_bits + 1;
         const uint32_t taddr0 = tb + ((uint32_t)(quad * 32) << 16) + (uint32_t)(colchunk * 64);
-        const float* thr_col = hp.thr_pre_col + (size_t)first_blk * 128 + quad * 32 + lane;
-        int gcount = 0, cnt = 0, nst = 0;
+        const size_t col0 = (size_t)first_blk * 128 + quad * 32 + lane;
+        // candidate slots: the block being filled [cbase, cbase + kTc5CandBlock) and the next one, reserved in advance
+        unsigned long long cbase = 0, nbase = 0;
+        if (lane == 0) {
+            cbase = atomicAdd(&p.counters[SMG_CTR_CANDIDATES], 2ull * kTc5CandBlock);
+            nbase = cbase + kTc5CandBlock;
+        }
+        cbase = __shfl_sync(SMG_FULL_MASK, cbase, 0);
+        nbase = __shfl_sync(SMG_FULL_MASK, nbase, 0);
+        int cused = 0;
+        int gcount = 0;
         for (int ci = blockIdx.x; ci < hp.n_chunks; ci += gridDim.x) {
             const smg_chunk_t ch = p.chunks[ci];
-            const smg_row_t row = p.rows[ch.row];
-            const int c0 = ch.start, c1 = min(c0 + p.chunk_len, row.n_own);
+            const int c0 = ch.start, c1 = min(c0 + p.chunk_len, p.rows[ch.row].n_own);
             const unsigned long long rowbits = (unsigned long long)(unsigned)ch.row << hp.cand_shift;
-            int tile = 0;
-            for (int t0 = c0; t0 < c1; t0 += kTc5Tile, ++tile) {
+            for (int t0 = c0; t0 < c1; t0 += kTc5Tile) {
                 for (int b = 0; b < n_blk; ++b) {
-                    const float thr = thr_col[b * 128];
+                    const float thr = hp.thr_pre_col[col0 + b * 128];
+                    const int cid = hp.col_id[col0 + b * 128];
                     for (int e = 0; e < 2; ++e, ++gcount) {
                         const int buf = gcount & 1;
                         tc5::mbar_wait(&ms.tfull[buf], (uint32_t)((gcount >> 1) & 1));
                         tc5::fence_after_sync();
-                        const uint32_t tagbase = ((uint32_t)tile << 14) | ((uint32_t)b << 8) | ((uint32_t)e << 7) | (uint32_t)lane;
                         // two halves of 32 cells: 18 warps leave 96 registers per thread (5 warps share a 16 K sub-partition)
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
@@ -317,7 +261,6 @@ __global__ void __launch_bounds__(kTc5Threads, 1) scan_tc5_kernel(const __grid_c
                             }
 #pragma unroll
                             for (int gh = 0; gh < 2; ++gh) {
-                                const int g = half * 2 + gh;
                                 const float* v = reinterpret_cast<const float*>(r) + 16 * gh;
                                 const float m0 = tc5_max3(v[0], v[1], v[2]), m1 = tc5_max3(v[3], v[4], v[5]);
                                 const float m2 = tc5_max3(v[6], v[7], v[8]), m3 = tc5_max3(v[9], v[10], v[11]);
@@ -326,35 +269,56 @@ __global__ void __launch_bounds__(kTc5Threads, 1) scan_tc5_kernel(const __grid_c
                                 const bool hot = gm > thr;
                                 const unsigned bm = __ballot_sync(SMG_FULL_MASK, hot);
                                 if (bm) {
+                                    // ---- transpose: flagged lanes -> scratch entries, then lane = cell, two entries per ballot
+                                    const int k = __popc(bm);
                                     if (hot) {
-                                        const int slot = cnt + __popc(bm & lt_mask);
-                                        float4* dst = reinterpret_cast<float4*>(qv + slot * 16);
+                                        float4* dst = reinterpret_cast<float4*>(scratch + __popc(bm & lt_mask) * kTc5EntryBytes);
                                         dst[0] = make_float4(v[0], v[1], v[2], v[3]);
                                         dst[1] = make_float4(v[4], v[5], v[6], v[7]);
                                         dst[2] = make_float4(v[8], v[9], v[10], v[11]);
                                         dst[3] = make_float4(v[12], v[13], v[14], v[15]);
-                                        qt[slot] = tagbase | ((uint32_t)g << 5);
+                                        reinterpret_cast<uint2*>(dst)[8] = make_uint2(__float_as_uint(thr), (uint32_t)cid);
                                     }
-                                    cnt += __popc(bm);
                                     __syncwarp();
-                                    if (cnt > kTc5QCap - 32) {
-                                        nst = tc5_drain(dr, cnt, nst, c0, c1, rowbits, lane);
-                                        cnt = 0;
-                                        __syncwarp();
+                                    const int s0 = t0 + 2 * (colchunk * 64 + (half * 2 + gh) * 16) + e;  // window start of cell 0
+                                    const bool cell_ok = s0 + 2 * cell < c1;                           // starts owned by this chunk
+                                    for (int j = 0; j < k; j += 2) {
+                                        const uint8_t* ent = scratch + (j + sub) * kTc5EntryBytes;
+                                        const uint2 tc = reinterpret_cast<const uint2*>(ent)[8];
+                                        const float val = reinterpret_cast<const float*>(ent)[cell];
+                                        const bool is = cell_ok && (j + sub < k) && (val > __uint_as_float(tc.x));
+                                        const unsigned m = __ballot_sync(SMG_FULL_MASK, is);
+                                        if (m) {
+                                            if (is) {
+                                                const int i = cused + __popc(m & lt_mask);
+                                                const unsigned long long idx = i < kTc5CandBlock ? cbase + i : nbase + (i - kTc5CandBlock);
+                                                if (idx < hp.cand_cap)
+                                                    hp.cand[idx] = rowbits | ((unsigned long long)(unsigned)(s0 + 2 * cell) << pos_shift) |
+                                                                   (unsigned long long)tc.y;
+                                            }
+                                            cused += __popc(m);
+                                            if (cused >= kTc5CandBlock) {  // move on to the reserved block, reserve another one
+                                                cused -= kTc5CandBlock;
+                                                cbase = nbase;
+                                                unsigned long long nb = 0;
+                                                if (lane == 0) nb = atomicAdd(&p.counters[SMG_CTR_CANDIDATES], (unsigned long long)kTc5CandBlock);
+                                                nbase = __shfl_sync(SMG_FULL_MASK, nb, 0);
+                                            }
+                                        }
                                     }
+                                    __syncwarp();  // the scratch is rewritten by the next flagged group
                                 }
                             }
                         }
                     }
                 }
             }
-            if (cnt > 0) {  // tags are chunk-relative: drain before the next chunk
-                nst = tc5_drain(dr, cnt, nst, c0, c1, rowbits, lane);
-                cnt = 0;
-                __syncwarp();
-            }
         }
-        if (nst > 0) nst = tc5_flush(hp, stage, nst, lane);
+        // pad what was reserved and not used (the exact pass walks every reserved slot)
+        for (int i = cused + lane; i < 2 * kTc5CandBlock; i += 32) {
+            const unsigned long long idx = i < kTc5CandBlock ? cbase + i : nbase + (i - kTc5CandBlock);
+            if (idx < hp.cand_cap) hp.cand[idx] = SMG_CAND_INVALID;
+        }
     }
     tc5::fence_before_sync();
     __syncthreads();

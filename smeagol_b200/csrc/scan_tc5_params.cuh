@@ -10,18 +10,18 @@ constexpr int kTc5Threads = 32 * (2 + kTc5EpiWarps);
 constexpr int kTc5Tile = 512;                           // window starts per tile (2 accumulators of 256: even / odd)
 constexpr int kTc5StripBases = 544;                     // 2 * 255 + 1 + 32 (widest PWM) rounded up to whole words
 constexpr int kTc5StripBytes = kTc5StripBases * 8;      // 4 fp16 per base
-constexpr int kTc5QCap = 48;                            // queue entries (16 cells each) per epilogue warp
-constexpr int kTc5Stage = 64;                           // staged 64-bit candidates per epilogue warp
+constexpr int kTc5EntryBytes = 80;                      // 16 accumulator cells + {threshold, column id} of one flagged lane
+constexpr int kTc5ScratchBytes = 32 * kTc5EntryBytes;   // per epilogue warp: the flagged lanes of one group of 16 cells
+constexpr int kTc5CandBlock = 128;                      // candidate slots an epilogue warp reserves per atomic
 constexpr int kTc5MaxBlk = 40;                          // 128-column blocks per column group
 // shared-memory carve-up (bytes)
 constexpr int kTc5OffStrip = 0;
-constexpr int kTc5OffQV = kTc5OffStrip + 4 * kTc5StripBytes;
-constexpr int kTc5OffQT = kTc5OffQV + kTc5EpiWarps * kTc5QCap * 64;
-constexpr int kTc5OffStage = kTc5OffQT + kTc5EpiWarps * kTc5QCap * 4;
-constexpr int kTc5OffMisc = kTc5OffStage + kTc5EpiWarps * kTc5Stage * 8;
+constexpr int kTc5OffScratch = kTc5OffStrip + 4 * kTc5StripBytes;
+constexpr int kTc5OffMisc = kTc5OffScratch + kTc5EpiWarps * kTc5ScratchBytes;
 constexpr int kTc5OffW = ((kTc5OffMisc + 1024 + 1023) / 1024) * 1024;  // weight image of the column group
 constexpr int kTc5MaxImageBytes = 232448 - kTc5OffW;                  // 227 KB per CTA
 constexpr int kTc5UnitBytes = 4096;                                   // 128 columns x one k16 step of fp16
+#define SMG_CAND_INVALID 0xffffffffffffffffull                        // padding of a reserved candidate block
 
 struct Tc5Params {
     ScanParams sp;

@@ -19,7 +19,7 @@ ROW_PAD_BASES = 96  # every row is followed by at least this many 'Z' bases (hal
 NEAR_REL = 1e-5     # half-width of the near-threshold band, relative to sum_k max_b |T[k,b]|
 STRANDS = {"none": 1, "only": 2, "both": 3}
 DEFAULT_ENGINE = "regtab"
-DEFAULT_TC_KIND = "hmma"  # tensor-core prefilter of the 'auto' / tensor-core engines: 'hmma' (mma.sync) or 'tc5' (tcgen05 + TMEM)
+DEFAULT_TC_KIND = "tc5"  # tensor-core prefilter of the 'auto' / tensor-core engines: 'hmma' (mma.sync) or 'tc5' (tcgen05 + TMEM)
 DEFAULT_TC_MIN_WIDTH = 7  # measured per width (profiles/r01_bench_widths.txt): the register-table engine wins up to W = 6 (hit density >= 6e-3 at thr 0.7), the tensor-core prefilter from W = 7
 
 
@@ -271,13 +271,17 @@ class ScanPlan:
 
     def __init__(self, pwmset, batch, thr64, strands, out_rows, n_out_rows, want_hits=True, want_counts=True,
                  adjudicate=True, chunk_len=None, hit_cap=None, near_cap=None, engine=None):
-        """engine: 'regtab' (fused FP32 register-table kernel) or 'hmma' (tensor-core prefilter + exact second pass;
-        same results).  Default: $SMEAGOL_B200_ENGINE or DEFAULT_ENGINE."""
+        """engine: 'regtab' (fused FP32 register-table kernel), 'hmma' (mma.sync tensor-core prefilter + exact second
+        pass) or 'tc5' (tcgen05 / TMEM prefilter + the same exact second pass); identical results.  Default:
+        $SMEAGOL_B200_ENGINE or DEFAULT_ENGINE; a PWM set built with a width split runs 'auto' (register-table kernel below
+        the split, the prefilter $SMEAGOL_B200_TC_KIND / DEFAULT_TC_KIND above it)."""
         self.lib = _lib.load()
         self.engine = engine or os.environ.get("SMEAGOL_B200_ENGINE", DEFAULT_ENGINE)
         self.tc_kind = os.environ.get("SMEAGOL_B200_TC_KIND", DEFAULT_TC_KIND)
-        if self.engine == "tc5":
+        if self.engine == "tc5":      # 'hmma' / 'tc5' name the prefilter explicitly; 'auto' takes the default kind
             self.engine, self.tc_kind = "hmma", "tc5"
+        elif self.engine == "hmma":
+            self.tc_kind = "hmma"
         if pwmset.tc_min_width > 0:
             self.engine = "auto"    # the PWM set was built split: both engines run, each on its side
         elif self.engine == "auto" or (self.engine == "hmma" and pwmset.n_wide > 0):
@@ -327,7 +331,8 @@ class ScanPlan:
             self.cand_pos_bits = _bits(int(batch.rows_host["n_avail"].max()) + 2)
             if self.cand_pos_bits + self.motif_bits + 1 + _bits(batch.n_rows) > 62:
                 raise ValueError("candidate key does not fit in 62 bits")
-            self.cand_cap = int(self.hit_cap * 1.25) + 4096
+            # tc5: every epilogue warp of every CTA keeps two blocks of 128 candidate slots reserved
+            self.cand_cap = int(self.hit_cap * 1.25) + 4096 + ((1 << 20) if self.tc_kind == "tc5" else 0)
         self._alloc()
 
     def _alloc(self):
@@ -437,7 +442,9 @@ def scan(pwmset, batch, thr64, strands, out_rows, n_out_rows, want_hits=True, wa
     return plan.finish(sort=sort)
 
 
-def sort_hits(keys, scores, n, key_bits, keys_out=None, scores_out=None, temp=None):
+def sort_hits(keys, scores, n, key_bits, keys_out=None, scores_out=None, temp=None, return_temp=False):
+    """Sort the first n (key, score) pairs into the reference's np.where order.  temp: reusable scratch (grown when too
+    small; pass return_temp=True to get the possibly re-allocated buffer back as a third result)."""
     lib = _lib.load()
     dev = keys.device
     if keys_out is None:
@@ -451,6 +458,8 @@ def sort_hits(keys, scores, n, key_bits, keys_out=None, scores_out=None, temp=No
     tb = ctypes.c_uint64(temp.numel())
     _lib.check(lib.smg_sort_hits(_ptr(keys), _ptr(scores), _ptr(keys_out), _ptr(scores_out), n, key_bits, _ptr(temp),
                                  ctypes.byref(tb), _stream()), "smg_sort_hits")
+    if return_temp:
+        return keys_out, scores_out, temp
     return keys_out, scores_out
 
 

@@ -100,24 +100,56 @@ def gather_hits(keys, scores, n_hits):
     return torch.cat([k[:c] for k, c in zip(kl, ns)]), torch.cat([s[:c] for s, c in zip(sl, ns)])
 
 
-def scan_long_sequence(seq_u8, model, frac_threshold, rcomp="both", seg_len=1 << 26, want_hits=True, chunk_len=None):
-    """Config-c4 style scan of ONE long sequence sharded over the ranks of the default process group.
+def long_sequence_batch(seq_u8, L, a, b, e, halo, seg_len=1 << 26):
+    """SeqBatch of one rank's range [a, b) (+ halo up to e) of a long sequence, cut into segments of seg_len owned
+    starts.  seq_u8: the full sequence as a uint8 ASCII numpy array, or a (pinned) torch uint8 tensor -- the tensor
+    route uploads the rank's range straight from that buffer (no host-side gather: segment starts are 16-aligned)."""
+    from . import device as dev
 
-    seq_u8: the full sequence as a uint8 ASCII array (every rank passes the same array, or at least its own range).
-    Each rank uploads only its range + halo, scans it (both strands fused; RC coordinates use the global length),
-    and the count table is all-reduced.  Returns (ScanResult with rank-local hits, global counts tensor (1, M, 2))."""
+    slices, segs = segment_rows(a, b, e, L, seg_len=seg_len, halo=halo)
+    if isinstance(seq_u8, torch.Tensor):
+        host = seq_u8[a:e]
+        src_off = np.array([lo - a for lo, _ in slices], dtype=np.int64)
+        lens = np.array([hi - lo for lo, hi in slices], dtype=np.int64)
+        return dev.SeqBatch(None, flat=(host, src_off, lens), segments=segs), segs
+    return dev.SeqBatch([seq_u8[lo:hi] for lo, hi in slices], segments=segs), segs
+
+
+def plan_long_sequence(seq_u8, model, frac_threshold, rcomp="both", seg_len=1 << 26, want_hits=True, chunk_len=None,
+                       hit_cap=None, engine=None):
+    """Upload + pack this rank's range of ONE long sequence and prepare its fused scan (config c4).  Returns
+    (ScanPlan, SeqBatch); plan.launch() / plan.finish() may be called repeatedly (benchmarks)."""
     from . import device as dev
 
     rank, world = world_info()
     L = int(seq_u8.shape[0])
     halo = int(model.max_width) - 1
     a, b, e = shard_sequence(L, world, halo)[rank]
-    slices, segs = segment_rows(a, b, e, L, seg_len=seg_len, halo=halo)
-    batch = dev.SeqBatch([seq_u8[lo:hi] for lo, hi in slices], segments=segs)
+    batch, segs = long_sequence_batch(seq_u8, L, a, b, e, halo, seg_len)
     n = len(segs)
     out_rows = np.stack([np.zeros(n), np.ones(n)], axis=1).astype(np.int32)
-    res = dev.scan(model.device_set, batch, model.thresholds(frac_threshold), dev.STRANDS[rcomp], out_rows, 2,
-                   want_hits=want_hits, want_counts=True, adjudicate=model.adjudicate, chunk_len=chunk_len)
-    counts = res.counts.sum(dim=0, keepdim=True).to(torch.int32)
-    allreduce_counts(counts)
-    return res, counts
+    plan = dev.ScanPlan(model.device_set, batch, model.thresholds(frac_threshold), dev.STRANDS[rcomp], out_rows, 2,
+                        want_hits=want_hits, want_counts=True, adjudicate=model.adjudicate, chunk_len=chunk_len,
+                        hit_cap=hit_cap, engine=engine)
+    return plan, batch
+
+
+def reduce_long_counts(plan):
+    """(segments, M, 2) per-rank count table -> global (1, M, 2) table: ONE all_reduce over NVLink."""
+    counts = plan.counts.sum(dim=0, keepdim=True).to(torch.int32)
+    return allreduce_counts(counts)
+
+
+def scan_long_sequence(seq_u8, model, frac_threshold, rcomp="both", seg_len=1 << 26, want_hits=True, chunk_len=None,
+                       hit_cap=None, sort=True):
+    """Config-c4 style scan of ONE long sequence sharded over the ranks of the default process group.
+
+    seq_u8: the full sequence as a uint8 ASCII array or pinned torch uint8 tensor (every rank passes the same buffer,
+    or at least its own range).  Each rank uploads only its range + halo, scans it (both strands fused; RC coordinates
+    use the global length), and the count table is all-reduced.  Returns (ScanResult with rank-local hits -- sorted,
+    keys in global coordinates --, global counts tensor (1, M, 2))."""
+    plan, _ = plan_long_sequence(seq_u8, model, frac_threshold, rcomp, seg_len, want_hits, chunk_len, hit_cap)
+    plan.launch()
+    res = plan.finish(sort=sort)
+    model.last_scan_stats = res.stats
+    return res, reduce_long_counts(plan)
