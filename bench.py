@@ -238,7 +238,7 @@ def load_traffic(key):
 def tensor_side_roofline(dset, total_bases, tc_ms, step_ms, peaks, peaks_kind, tc_kind, traffic):
     """Roofline of the tensor-core prefilter + exact second pass (the dominant side of the scan)."""
     w = dset.widths.astype(np.int64)
-    tc = (w >= dset.tc_min_width) & (w <= 32)
+    tc = (w >= max(dset.tc_min_width, dset.kmer_max_width + 1)) & (w <= 32)
     flops = total_bases * 2 * int((2 * 4 * w[tc]).sum())                  # 2 strands x 2 flop x 4W per base x motif
     flops_padded = total_bases * 2 * int((2 * 16 * ((w[tc] + 3) // 4)).sum())
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
@@ -247,7 +247,7 @@ def tensor_side_roofline(dset, total_bases, tc_ms, step_ms, peaks, peaks_kind, t
             else "smg::scan_hmma_kernel (mma.sync) + finalize_candidates_kernel")
     return {"bound": "tensor", "achieved": flops / tc_s / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": flops / tc_s / 1e12 / peak_tf, "traffic": traffic,
-            "kernel": "%s: %d PWMs of width >= %d" % (kern, int(tc.sum()), dset.tc_min_width),
+            "kernel": "%s: %d PWMs of width >= %d" % (kern, int(tc.sum()), max(dset.tc_min_width, dset.kmer_max_width + 1)),
             "kernel_ms": tc_ms, "kernel_share_of_step": tc_ms / step_ms,
             "algorithmic": "2 strands x 2 flop x 4*W per base x motif (one-hot contraction, SURVEY 8d); with K padded to the "
                            "16-row slices the tensor cores execute: %.1f TFLOP/s" % (flops_padded / tc_s / 1e12),
@@ -274,6 +274,7 @@ def run_c4(args, rank, world, local_rank, device, peaks, peaks_kind, warmup):
 
     # ---- device-resident plan (the rank's range packed once, untimed)
     plan, batch = sdist.plan_long_sequence(host, model, THRESHOLD, engine=args.engine)
+    dset = plan.pwmset  # the sibling set of this plan's engine split (k-mer index / register tables / tensor cores)
     plan.launch()
     res0 = plan.finish(sort=False)  # calibrates the hit buffer; the workload is deterministic
     n_hits = res0.n_hits
@@ -289,6 +290,9 @@ def run_c4(args, rank, world, local_rank, device, peaks, peaks_kind, warmup):
         plan.counters.zero_()
         plan.counts.zero_()
         if plan.engine == "auto":
+            plan.launch_kmer_side()
+            if ev:
+                ev[5].record()
             plan.launch_regtab_side()
             if ev:
                 ev[1].record()
@@ -298,6 +302,7 @@ def run_c4(args, rank, world, local_rank, device, peaks, peaks_kind, warmup):
         else:
             plan.launch()
             if ev:
+                ev[5].record()
                 ev[1].record()
                 ev[2].record()
         if n_hits:
@@ -319,7 +324,7 @@ def run_c4(args, rank, world, local_rank, device, peaks, peaks_kind, warmup):
     if world > 1:
         dist.barrier()
     sampler.t_start = time.perf_counter()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
     launches0 = _lib.launch_count()
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
@@ -330,7 +335,8 @@ def run_c4(args, rank, world, local_rank, device, peaks, peaks_kind, warmup):
     t_wall = time.perf_counter() - t_wall0
     launches = _lib.launch_count() - launches0
     step_ms = float(np.mean([e[0].elapsed_time(e[4]) for e in evs]))
-    regtab_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    kmer_ms = float(np.mean([e[0].elapsed_time(e[5]) for e in evs]))
+    regtab_ms = float(np.mean([e[5].elapsed_time(e[1]) for e in evs]))
     tc_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
     sort_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
     coll_ms = float(np.mean([e[3].elapsed_time(e[4]) for e in evs]))
@@ -387,12 +393,13 @@ def run_c4(args, rank, world, local_rank, device, peaks, peaks_kind, warmup):
         roofline = tensor_side_roofline(dset, my_bases, tc_ms, step_ms, peaks, peaks_kind, tc_kind, traffic)
         w = dset.widths.astype(np.int64)
         lookups = my_bases * 2 * int(w.sum())
-        roofline["step_breakdown_ms"] = {"register_table_side": regtab_ms, "tensor_core_side": tc_ms, "sort": sort_ms,
-                                         "count_sum_allreduce": coll_ms}
+        roofline["step_breakdown_ms"] = {"kmer_index_side": kmer_ms, "register_table_side": regtab_ms, "tensor_core_side": tc_ms,
+                                         "sort": sort_ms, "count_sum_allreduce": coll_ms}
         roofline["sort_dram_bytes"] = sort_bytes
         roofline["algorithmic_dram_bytes"] = int(my_bases * 0.375 + n_hits * 12 + M * 8)
-        roofline["fp32_pipe_view"] = {"Tlookup_add_per_s": lookups / ((regtab_ms + tc_ms) * 1e-3) / 1e12, "peak": FP32_ADD_PEAK_T,
-                                      "frac": lookups / ((regtab_ms + tc_ms) * 1e-3) / 1e12 / FP32_ADD_PEAK_T,
+        scan_ms = kmer_ms + regtab_ms + tc_ms
+        roofline["fp32_pipe_view"] = {"Tlookup_add_per_s": lookups / (scan_ms * 1e-3) / 1e12, "peak": FP32_ADD_PEAK_T,
+                                      "frac": lookups / (scan_ms * 1e-3) / 1e12 / FP32_ADD_PEAK_T,
                                       "note": "2*W lookup-adds per base x motif (SURVEY 8d) over the scan kernels of rank 0, against "
                                               "the measured FP32 add peak; the prefilter skips most lookups, so > 1 is possible"}
         line = {"metric": METRIC, "value": value, "unit": "Gbase*motif/s", "n_gpus": world, "steps": args.steps,
@@ -403,6 +410,8 @@ def run_c4(args, rank, world, local_rank, device, peaks, peaks_kind, warmup):
                             "count_table_sum": count_sum, "count_table_checksum": count_chk,
                             "rank0_hits": n_hits, "rank0_sorted": sorted_ok, "engine": model.last_scan_stats.get("engine"),
                             "tc_kind": tc_kind, "tc_min_width": dset.tc_min_width,
+                            "kmer_max_width": model.last_scan_stats.get("kmer_max_width"),
+                            "kmer_index_entries": model.last_scan_stats.get("kmer_index_entries"),
                             "near_threshold_adjudicated_rank0": int(c[_lib.CTR_NEAR] + c[_lib.CTR_NEAR_TC]),
                             "collective": "all_reduce(count table (1, M, 2) int32) per step" if world > 1 else "none"},
                 "roofline": roofline,
@@ -436,6 +445,7 @@ def run_c2(args, rank, world, local_rank, device, peaks, peaks_kind, warmup, ste
     batch = dev.SeqBatch(None, flat=(host_flat, src_off, lens))
     plan = dev.ScanPlan(dset, batch, thr, 3, out_rows, 2 * n, want_hits=True, want_counts=True, adjudicate=True,
                         engine=args.engine)
+    pset = plan.pwmset
     plan.launch()
     res0 = plan.finish(sort=True)
     n_hits = res0.n_hits
@@ -452,6 +462,7 @@ def run_c2(args, rank, world, local_rank, device, peaks, peaks_kind, warmup, ste
         plan.counters.zero_()
         plan.counts.zero_()
         if plan.engine == "auto":
+            plan.launch_kmer_side()
             plan.launch_regtab_side()
             if ev:
                 ev[1].record()
@@ -515,14 +526,15 @@ def run_c2(args, rank, world, local_rank, device, peaks, peaks_kind, warmup, ste
     e2e_t = allreduce_max(float(np.mean(e2e_times)), world, device)
     out = {"workload": C2_WORKLOAD, "value": value, "unit": "Gbase*motif/s", "ms_per_step": ms_per_step, "steps": steps,
            "scaling": "weak", "n_hits_per_gpu": n_hits, "hit_density": n_hits / (2.0 * units), "gpu_launches": int(launches),
-           "step_breakdown_ms": {"register_table_side": regtab_ms, "tensor_core_side": tc_ms, "sort_and_collective": sort_ms},
-           "engine": stats.get("engine"), "tc_kind": stats.get("tc_kind"),
+           "step_breakdown_ms": {"kmer_index_and_register_table_side": regtab_ms, "tensor_core_side": tc_ms,
+                                 "sort_and_collective": sort_ms},
+           "engine": stats.get("engine"), "tc_kind": stats.get("tc_kind"), "kmer_max_width": stats.get("kmer_max_width"),
            "e2e_device_api": {"value": units * world / e2e_t / 1e9, "ms_per_step": e2e_t * 1e3,
                               "h2d_bytes_per_step": int(batch.h2d_bytes + batch.n_rows * 40),
                               "d2h_bytes_per_step": int(plan.counts.numel() * 4 + 64),
                               "note": "H2D ASCII genomes (pinned) + pack + scan + sort + D2H count table; site list stays on device"}}
     if rank == 0:
-        out["roofline"] = tensor_side_roofline(dset, total_bases, tc_ms, step_ms, peaks, peaks_kind, stats.get("tc_kind") or "hmma",
+        out["roofline"] = tensor_side_roofline(pset, total_bases, tc_ms, step_ms, peaks, peaks_kind, stats.get("tc_kind") or "hmma",
                                                load_traffic("c2_dominant_kernel_dram_bytes"))
     if with_frames and rank == 0:
         # the PUBLIC call, like for like with the reference arm: records in, `counts` (and `sites`) DataFrames out

@@ -68,7 +68,18 @@ typedef struct {
 #define SMG_CTR_CANDIDATES 5    /* smg_scan_tc: candidates emitted by the tensor-core prefilter (> cand_cap: overflow) */
 #define SMG_CTR_NEAR_TC 6       /* smg_scan_tc: near-threshold candidates adjudicated inside its exact pass (a tally: they
                                    never occupy d_near, so they do not count against near_cap) */
+#define SMG_CTR_KMER_ENTRIES 7   /* smg_kmer_index_build: entries written (> entry_cap: overflow, rebuild with a larger buffer) */
 #define SMG_N_COUNTERS 8
+
+/* one (k-mer, PWM, strand) hit of the k-mer index: col = motif * 2 + strand | flags (bit 30: decided by the fp64
+ * adjudicator, bit 29: rejected by it), score = the fp32 window score, next = next entry of the same k-mer or -1 */
+typedef struct {
+    uint32_t col;
+    float score;
+    int32_t next;
+    int32_t reserved;
+} smg_kmer_entry_t;
+#define SMG_KMER_MAX_WIDTH 12
 
 int smg_version(void);
 const char* smg_last_error(void);
@@ -86,6 +97,12 @@ int smg_pwmset_create(const float* h_weights, const int32_t* h_widths, int32_t n
  * same hit / count / counter buffers.  With tc_min_width = 0 either entry point alone covers every PWM. */
 int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int32_t n_motifs, int32_t tc_min_width,
                             smg_pwmset_t* out);
+/* Three-engine split: PWMs narrower than regtab_min_width belong to the k-mer index engine alone (smg_scan_kmer with
+ * kmer_max_width = regtab_min_width - 1), those in [regtab_min_width, tc_min_width) and those wider than
+ * SMG_MAX_REGTAB_WIDTH to smg_scan, those in [tc_min_width, SMG_MAX_REGTAB_WIDTH] to smg_scan_tc / smg_scan_tc5.
+ * regtab_min_width = 0 or 1: no k-mer engine (same as smg_pwmset_create_split). */
+int smg_pwmset_create_split3(const float* h_weights, const int32_t* h_widths, int32_t n_motifs, int32_t regtab_min_width,
+                             int32_t tc_min_width, smg_pwmset_t* out);
 int smg_pwmset_destroy(smg_pwmset_t set);
 /* info[0]=n_motifs info[1]=max_width info[2]=n_regtab_groups info[3]=n_buckets info[4]=n_wide_motifs
  * info[5]=sum over groups of padded width (dual groups count both strands) info[6]=128-column blocks and
@@ -176,6 +193,25 @@ int smg_scan_tc5(smg_pwmset_t set, const uint32_t* d_packed, const uint16_t* d_a
                  const float* d_thr_pre, const double* d_thr64, int pos_bits, int motif_bits, int cand_pos_bits,
                  uint64_t* d_cand, uint64_t cand_cap, uint64_t* d_hit_keys, float* d_hit_scores, uint64_t hit_cap,
                  int32_t* d_counts, uint64_t* d_counters, void* stream);
+
+/* K-mer index engine for PWMs of width <= kmer_max_width <= SMG_KMER_MAX_WIDTH (smeagol_b200/csrc/kmer.cu): the same
+ * contract and results as smg_scan + smg_adjudicate for those PWMs (hits, fp32 scores, counts, counters), computed by
+ * scoring every k-mer of every width class once per call (smg_kmer_index_build: fp32 in the fixed order, near-threshold
+ * band adjudicated in fp64) and then looking window contents up (smg_scan_kmer); windows holding IUPAC codes are scored
+ * directly.  The index depends on the thresholds and the strand mask; it is valid for any sequences.
+ *  smg_kmer_index_size: *head_len = int32 slots of d_head for this PWM set and kmer_max_width.
+ *  smg_kmer_index_build: d_head (head_len int32) and d_entries (entry_cap) are written; d_counters[SMG_CTR_KMER_ENTRIES]
+ *      (zeroed by the caller) = entries needed (> entry_cap: rebuild with a larger buffer). */
+int smg_kmer_index_size(smg_pwmset_t set, int kmer_max_width, int64_t* head_len);
+int smg_kmer_index_build(smg_pwmset_t set, int kmer_max_width, int strands, const float* d_thr_lo, const float* d_thr_hi,
+                         const double* d_thr64, int32_t* d_head, int64_t head_len, smg_kmer_entry_t* d_entries,
+                         uint64_t entry_cap, uint64_t* d_counters, void* stream);
+int smg_scan_kmer(smg_pwmset_t set, int kmer_max_width, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
+                  const smg_row_t* d_rows, int32_t n_rows, const int32_t* d_out_rows, const smg_chunk_t* d_chunks,
+                  int32_t n_chunks, int32_t chunk_len, int strands, const float* d_thr_lo, const float* d_thr_hi,
+                  const double* d_thr64, int pos_bits, int motif_bits, const int32_t* d_head, const smg_kmer_entry_t* d_entries,
+                  uint64_t entry_cap, uint64_t* d_hit_keys, float* d_hit_scores, uint64_t hit_cap, int32_t* d_counts,
+                  uint64_t* d_counters, void* stream);
 
 /* fp64 adjudication of the near-threshold candidates: score64 = sum of the fp32 operands in double, hit iff
  * score64 > d_thr64[motif] (thr = frac * max_scores computed on the host as models.py:141 does). */

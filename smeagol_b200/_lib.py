@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SMEAGOL_B200_LIB", os.path.join(_HERE, "libsmeagol_b200.so"))  # env: tuning builds
 
 SMG_OK = 0
-CTR_HITS_APPENDED, CTR_NEAR, CTR_DEFINITE, CTR_ADJ_ACCEPTED, CTR_LAUNCHES, CTR_CANDIDATES, CTR_NEAR_TC = 0, 1, 2, 3, 4, 5, 6
+CTR_HITS_APPENDED, CTR_NEAR, CTR_DEFINITE, CTR_ADJ_ACCEPTED, CTR_LAUNCHES, CTR_CANDIDATES, CTR_NEAR_TC, CTR_KMER_ENTRIES = 0, 1, 2, 3, 4, 5, 6, 7
 N_COUNTERS = 8
 MAX_REGTAB_WIDTH = 32
 ROW_DTYPE_FIELDS = [("word_off", "<i8"), ("g_off", "<i8"), ("g_len", "<i8"), ("n_avail", "<i4"), ("n_own", "<i4")]
@@ -17,7 +17,8 @@ NEAR_BYTES = 24
 
 # every symbol include/smeagol_b200.h declares (tests/test_cabi.py checks the export list against the header)
 EXPORTS = [
-    "smg_version", "smg_last_error", "smg_launch_count", "smg_pwmset_create", "smg_pwmset_create_split", "smg_pwmset_destroy", "smg_pwmset_info",
+    "smg_version", "smg_last_error", "smg_launch_count", "smg_pwmset_create", "smg_pwmset_create_split", "smg_pwmset_create_split3",
+    "smg_kmer_index_size", "smg_kmer_index_build", "smg_scan_kmer", "smg_pwmset_destroy", "smg_pwmset_info",
     "smg_pack", "smg_scan", "smg_scan_tc", "smg_scan_tc5", "smg_adjudicate", "smg_sort_hits", "smg_predict_dense", "smg_variant_sites",
     "smg_variant_windows", "smg_fasta_index", "smg_fasta_compact", "smg_kmer_shuffle", "smg_bin_hits",
 ]
@@ -46,6 +47,11 @@ def load():
     lib.smg_launch_count.restype = u64
     lib.smg_pwmset_create.argtypes = [vp, vp, i32, ctypes.POINTER(vp)]
     lib.smg_pwmset_create_split.argtypes = [vp, vp, i32, i32, ctypes.POINTER(vp)]
+    lib.smg_pwmset_create_split3.argtypes = [vp, vp, i32, i32, i32, ctypes.POINTER(vp)]
+    lib.smg_kmer_index_size.argtypes = [vp, ctypes.c_int, ctypes.POINTER(i64)]
+    lib.smg_kmer_index_build.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, i64, vp, u64, vp, vp]
+    lib.smg_scan_kmer.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, i32, vp, vp, i32, i32, ctypes.c_int, vp, vp, vp, ctypes.c_int,
+                                  ctypes.c_int, vp, vp, u64, vp, vp, u64, vp, vp, vp]
     lib.smg_pwmset_destroy.argtypes = [vp]
     lib.smg_pwmset_info.argtypes = [vp, vp]
     lib.smg_pack.argtypes = [vp, ctypes.c_int, vp, vp, i32, i64, vp, vp, vp, vp, vp]

@@ -18,6 +18,7 @@
 #include <cuda_fp16.h>
 #include "variant_launchers.h"
 #include "scan_tc5_params.cuh"
+#include "kmer.h"
 #include "tc5_launchers.h"
 
 // ------------------------------------------------------------------------------------------ host-side state
@@ -70,6 +71,8 @@ struct smg_pwmset {
     std::vector<HmmaBucket> hbuckets;
     int64_t n_hcols = 0;
     int split = 0;  // > 0: smg_scan covers PWMs narrower than this, smg_scan_tc the others (hybrid engine)
+    int kmin = 0;   // > 1: PWMs narrower than this belong to the k-mer index engine alone (in no lane group / fragment table)
+    int32_t* d_cls_motifs = nullptr;  // motif ids sorted by width (k-mer index classes)
     uint32_t* d_afrag = nullptr;
     int64_t* d_cg_afrag_off = nullptr;
     int32_t* d_col_id = nullptr;
@@ -193,67 +196,6 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ s
         }
         if (any_amb) status[1] = 1ull;
     }
-}
-
-// score of one window on the forward string, strand st, fp32 ascending-k order (same order as the register kernel)
-__device__ float window_score32(const ScanParams& p, const smg_row_t& row, const int motif, const int st, const int64_t s)
-{
-    const int wm = p.motif_width[motif];
-    const float* tab = p.nat_tab + p.motif_off[motif] * 4;
-    float acc = 0.f;
-    for (int k = 0; k < wm; ++k) {
-        const int c = smg_fetch_code(p.packed, p.amask, p.codes, row, s + k);
-        const float* tr = tab + (st ? (wm - 1 - k) : k) * 4;
-        const float t0 = st ? tr[3] : tr[0], t1 = st ? tr[2] : tr[1], t2 = st ? tr[1] : tr[2], t3 = st ? tr[0] : tr[3];
-        const float term = smg_mix(c_emb[c][0], c_emb[c][1], c_emb[c][2], c_emb[c][3], t0, t1, t2, t3);
-        acc = (k == 0) ? term : __fadd_rn(acc, term);
-    }
-    return acc;
-}
-
-// Same value as window_score32 (bit for bit) for a window of plain A/C/G/T bases that lies inside the row, W <= 32:
-// the bases come from three packed words held in registers, one table load + one add per PWM row.  Returns false when
-// the window needs the general path (ambiguity codes, 'Z', end padding, wider PWM).
-__device__ __forceinline__ bool window_score32_acgt(const ScanParams& p, const smg_row_t& row, const int motif, const int st,
-                                                    const int64_t s, float* out)
-{
-    const int wm = p.motif_width[motif];
-    if (wm > 32 || s < 0 || s + wm > row.n_avail) return false;
-    const int64_t w0 = row.word_off + (s >> 4);
-    if ((p.amask[w0] | p.amask[w0 + 1] | p.amask[w0 + 2]) != 0) return false;  // rows are padded: w0 + 2 is allocated
-    const int sh = 2 * (int)(s & 15);
-    const unsigned long long lo = (unsigned long long)p.packed[w0] | ((unsigned long long)p.packed[w0 + 1] << 32);
-    const unsigned long long hi = (unsigned long long)p.packed[w0 + 2];
-    unsigned long long win = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
-    const float* tab = p.nat_tab + p.motif_off[motif] * 4;
-    const int last = 4 * wm - 1;
-    // forward: T[k][b]; reverse complement on the forward string: T[W-1-k][3-b] = flat index (4W-1) - (4k+b).
-    // Ascending k, one rounded add per row: the summation order of the register-table kernel's ACGT path.
-    float acc = 0.f;
-    for (int k = 0; k < wm; ++k) {
-        const int j = 4 * k + (int)(win & 3ull);
-        win >>= 2;
-        const float term = tab[st ? (last - j) : j];
-        acc = (k == 0) ? term : __fadd_rn(acc, term);
-    }
-    *out = acc;
-    return true;
-}
-
-__device__ double window_score64(const uint32_t* packed, const uint16_t* amask, const uint8_t* codes, const smg_row_t& row,
-                                 const float* tab, const int wm, const int st, const int64_t s, const int64_t sub_pos,
-                                 const int sub_code)
-{
-    double acc = 0.0;
-    for (int k = 0; k < wm; ++k) {
-        int c = smg_fetch_code(packed, amask, codes, row, s + k);
-        if (s + k == sub_pos) c = sub_code;
-        const float* tr = tab + (st ? (wm - 1 - k) : k) * 4;
-        const float t0 = st ? tr[3] : tr[0], t1 = st ? tr[2] : tr[1], t2 = st ? tr[1] : tr[2], t3 = st ? tr[0] : tr[3];
-        const double term = smg_mix64(c, t0, t1, t2, t3);
-        acc = (k == 0) ? term : __dadd_rn(acc, term);
-    }
-    return acc;
 }
 
 // Fallback for PWMs wider than SMG_MAX_REGTAB_WIDTH: one thread per window start, tables from global memory.
@@ -573,7 +515,17 @@ int smg_pwmset_create(const float* h_weights, const int32_t* h_widths, int32_t n
 int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int32_t n_motifs, int32_t tc_min_width,
                             smg_pwmset_t* out)
 {
+    return smg_pwmset_create_split3(h_weights, h_widths, n_motifs, 0, tc_min_width, out);
+}
+
+int smg_pwmset_create_split3(const float* h_weights, const int32_t* h_widths, int32_t n_motifs, int32_t regtab_min_width,
+                             int32_t tc_min_width, smg_pwmset_t* out)
+{
     if (!h_weights || !h_widths || n_motifs <= 0 || !out) return fail(SMG_ERR_INVALID, "smg_pwmset_create: bad argument");
+    if (regtab_min_width < 0 || regtab_min_width > SMG_KMER_MAX_WIDTH + 1)
+        return fail(SMG_ERR_INVALID, "smg_pwmset_create_split3: regtab_min_width must be in 0..13");
+    if (regtab_min_width > 1 && tc_min_width > 0 && tc_min_width < regtab_min_width)
+        return fail(SMG_ERR_INVALID, "smg_pwmset_create_split3: tc_min_width must not be below regtab_min_width");
     if (tc_min_width < 0 || tc_min_width > SMG_MAX_REGTAB_WIDTH + 1)
         return fail(SMG_ERR_INVALID, "smg_pwmset_create_split: tc_min_width must be 0 (no split) or a width in 1..33");
     int rc = init_lut();
@@ -581,6 +533,7 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
     smg_pwmset* s = new smg_pwmset();
     s->n_motifs = n_motifs;
     s->split = tc_min_width;
+    s->kmin = regtab_min_width;
     s->widths.assign(h_widths, h_widths + n_motifs);
     s->offs.resize(n_motifs);
     int64_t tot = 0;
@@ -617,7 +570,7 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
         for (int w = 1; w <= kDualMaxWidth; ++w) {
             bool any = false;
             for (int m = 0; m < n_motifs; ++m)
-                if (h_widths[m] == w) { pool.push_back(m); any = true; }
+                if (h_widths[m] == w && w >= s->kmin) { pool.push_back(m); any = true; }
             if (any) last_w = w;
             const int nm = (std::max(w, 2) <= kPairMaxWidth) ? 2 : 1;
             while (pool.size() >= (size_t)32 * nm) emit_group(w, nm, (size_t)32 * nm);
@@ -692,7 +645,7 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
         for (int ks = 1; ks <= SMG_MAX_REGTAB_WIDTH / 4; ++ks) {
             std::vector<int> cols;  // motif * 2 + strand
             for (int m = 0; m < n_motifs; ++m)
-                if ((h_widths[m] + 3) / 4 == ks && (s->split == 0 || h_widths[m] >= s->split)) {  // tensor-core side only
+                if ((h_widths[m] + 3) / 4 == ks && (s->split == 0 || h_widths[m] >= s->split) && h_widths[m] >= s->kmin) {  // tensor-core side only
                     cols.push_back(m * 2);
                     cols.push_back(m * 2 + 1);
                 }
@@ -744,7 +697,7 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
         std::vector<int> cols;  // motif * 2 + strand, ascending K depth
         for (int ks = 1; ks <= SMG_MAX_REGTAB_WIDTH / 4; ++ks)
             for (int m = 0; m < n_motifs; ++m)
-                if ((h_widths[m] + 3) / 4 == ks && (s->split == 0 || h_widths[m] >= s->split)) {
+                if ((h_widths[m] + 3) / 4 == ks && (s->split == 0 || h_widths[m] >= s->split) && h_widths[m] >= s->kmin) {
                     cols.push_back(m * 2);
                     cols.push_back(m * 2 + 1);
                 }
@@ -815,6 +768,10 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
         s->t5_n_blocks = n_blocks;
         s->t5_n_groups = n_groups;
     }
+    std::vector<int32_t> cls_motifs;
+    for (int w = 1; w <= SMG_KMER_MAX_WIDTH; ++w)
+        for (int m = 0; m < n_motifs; ++m)
+            if (h_widths[m] == w) cls_motifs.push_back(m);
     std::vector<float> nat(h_weights, h_weights + tot * 4);
     std::vector<int32_t> wv(h_widths, h_widths + n_motifs);
     std::vector<int32_t> widev(s->wide.begin(), s->wide.end());
@@ -829,6 +786,7 @@ int smg_pwmset_create_split(const float* h_weights, const int32_t* h_widths, int
         (rc = upload(&s->d_t5_cg_first_blk, t5_cg_first_blk)) || (rc = upload(&s->d_t5_blk_ks, t5_blk_ks)) ||
         (rc = upload(&s->d_t5_blk_off, t5_blk_off)) || (rc = upload(&s->d_t5_col_id, t5_col_id)) ||
         (rc = upload(&s->d_t5_thr_pre_col, std::vector<float>((size_t)std::max(s->t5_n_blocks * 128, 1), 0.f))) ||
+        (rc = upload(&s->d_cls_motifs, cls_motifs)) ||
         (rc = upload(&s->d_wide, widev)) || (rc = upload(&s->d_dual_list, dualv)) || (rc = upload(&s->d_nondual_list, nondualv))) {
         smg_pwmset_destroy(s);
         return rc;
@@ -841,6 +799,7 @@ int smg_pwmset_destroy(smg_pwmset_t s)
 {
     if (!s) return SMG_OK;
     cudaFree(s->d_nat); cudaFree(s->d_width); cudaFree(s->d_off); cudaFree(s->d_gtab); cudaFree(s->d_gtab_off);
+    cudaFree(s->d_cls_motifs);
     cudaFree(s->d_t5_img); cudaFree(s->d_t5_cg_img_off); cudaFree(s->d_t5_cg_first_blk); cudaFree(s->d_t5_blk_ks);
     cudaFree(s->d_t5_blk_off); cudaFree(s->d_t5_col_id); cudaFree(s->d_t5_thr_pre_col);
     cudaFree(s->d_lane_motif); cudaFree(s->d_afrag); cudaFree(s->d_cg_afrag_off); cudaFree(s->d_col_id); cudaFree(s->d_thr_pre_col); cudaFree(s->d_wide); cudaFree(s->d_dual_list); cudaFree(s->d_nondual_list);
@@ -1045,6 +1004,73 @@ int smg_scan_tc5(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_ama
     return SMG_OK;
 }
 
+int smg_kmer_index_size(smg_pwmset_t s, int kmer_max_width, int64_t* head_len)
+{
+    if (!s || !head_len || kmer_max_width < 1 || kmer_max_width > SMG_KMER_MAX_WIDTH)
+        return fail(SMG_ERR_INVALID, "smg_kmer_index_size: bad argument");
+    *head_len = smg_kmer_head_len(s->widths, kmer_max_width);
+    return SMG_OK;
+}
+
+int smg_kmer_index_build(smg_pwmset_t s, int kmer_max_width, int strands, const float* d_thr_lo, const float* d_thr_hi,
+                         const double* d_thr64, int32_t* d_head, int64_t head_len, smg_kmer_entry_t* d_entries,
+                         uint64_t entry_cap, uint64_t* d_counters, void* stream)
+{
+    if (!s || kmer_max_width < 1 || kmer_max_width > SMG_KMER_MAX_WIDTH || !d_thr_lo || !d_thr_hi || !d_thr64 || !d_head ||
+        !d_entries || entry_cap == 0 || entry_cap > 0x7fffffffull || !d_counters)
+        return fail(SMG_ERR_INVALID, "smg_kmer_index_build: bad argument");
+    if ((strands & 3) == 0 || (strands & ~3)) return fail(SMG_ERR_INVALID, "smg_kmer_index_build: strands must be 1, 2 or 3");
+    if (head_len != smg_kmer_head_len(s->widths, kmer_max_width)) return fail(SMG_ERR_INVALID, "smg_kmer_index_build: head_len mismatch");
+    if (head_len == 0) return SMG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    smg::KmerParams kp;
+    memset(&kp, 0, sizeof(kp));
+    fill_params(kp.sp, s, nullptr, nullptr, nullptr, nullptr, nullptr);
+    kp.sp.strands = strands; kp.sp.thr_lo = d_thr_lo; kp.sp.thr_hi = d_thr_hi;
+    kp.sp.counters = reinterpret_cast<unsigned long long*>(d_counters);
+    if (smg_kmer_fill_params(kp, s->widths, s->d_cls_motifs, kmer_max_width)) return fail(SMG_ERR_INVALID, "smg_kmer_index_build: bad width");
+    kp.head = d_head; kp.entries = d_entries; kp.entry_cap = entry_cap; kp.thr64 = d_thr64;
+    SMG_CUDA(cudaMemsetAsync(d_head, 0xff, (size_t)head_len * sizeof(int32_t), st));
+    uint64_t nl = 0;
+    cudaError_t e = smg_kmer_launch_build(kp, st, &nl);
+    g_launches += nl;
+    if (e != cudaSuccess) return fail(SMG_ERR_CUDA, std::string("kmer_build_kernel: ") + cudaGetErrorString(e));
+    return SMG_OK;
+}
+
+int smg_scan_kmer(smg_pwmset_t s, int kmer_max_width, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
+                  const smg_row_t* d_rows, int32_t n_rows, const int32_t* d_out_rows, const smg_chunk_t* d_chunks,
+                  int32_t n_chunks, int32_t chunk_len, int strands, const float* d_thr_lo, const float* d_thr_hi,
+                  const double* d_thr64, int pos_bits, int motif_bits, const int32_t* d_head, const smg_kmer_entry_t* d_entries,
+                  uint64_t entry_cap, uint64_t* d_hit_keys, float* d_hit_scores, uint64_t hit_cap, int32_t* d_counts,
+                  uint64_t* d_counters, void* stream)
+{
+    if (!s || kmer_max_width < 1 || kmer_max_width > SMG_KMER_MAX_WIDTH || !d_packed || !d_amask || !d_rows || n_rows <= 0 ||
+        !d_out_rows || !d_chunks || n_chunks < 0 || !d_thr_lo || !d_thr_hi || !d_thr64 || !d_head || !d_entries || !d_counters)
+        return fail(SMG_ERR_INVALID, "smg_scan_kmer: bad argument");
+    if (chunk_len <= 0 || (chunk_len & 15)) return fail(SMG_ERR_INVALID, "smg_scan_kmer: chunk_len must be a positive multiple of 16");
+    if ((strands & 3) == 0 || (strands & ~3)) return fail(SMG_ERR_INVALID, "smg_scan_kmer: strands must be 1, 2 or 3");
+    if (pos_bits <= 0 || motif_bits <= 0 || pos_bits + motif_bits > 63) return fail(SMG_ERR_INVALID, "smg_scan_kmer: bad key layout");
+    if ((1ll << motif_bits) < s->n_motifs) return fail(SMG_ERR_INVALID, "smg_scan_kmer: motif_bits too small");
+    if ((d_hit_keys == nullptr) != (d_hit_scores == nullptr)) return fail(SMG_ERR_INVALID, "smg_scan_kmer: hit buffers must both be set or NULL");
+    if (n_chunks == 0 || smg_kmer_head_len(s->widths, kmer_max_width) == 0) return SMG_OK;
+    smg::KmerParams kp;
+    memset(&kp, 0, sizeof(kp));
+    fill_params(kp.sp, s, d_packed, d_amask, d_codes, d_rows, d_out_rows);
+    ScanParams& p = kp.sp;
+    p.chunks = d_chunks; p.chunk_len = chunk_len; p.strands = strands; p.thr_lo = d_thr_lo; p.thr_hi = d_thr_hi;
+    p.pos_bits = pos_bits; p.motif_bits = motif_bits;
+    p.hit_keys = reinterpret_cast<unsigned long long*>(d_hit_keys); p.hit_scores = d_hit_scores; p.hit_cap = hit_cap;
+    p.counts = d_counts; p.counters = reinterpret_cast<unsigned long long*>(d_counters);
+    if (smg_kmer_fill_params(kp, s->widths, s->d_cls_motifs, kmer_max_width)) return fail(SMG_ERR_INVALID, "smg_scan_kmer: bad width");
+    kp.head = const_cast<int32_t*>(d_head); kp.entries = const_cast<smg_kmer_entry_t*>(d_entries); kp.entry_cap = entry_cap;
+    kp.thr64 = d_thr64;
+    cudaError_t e = smg_kmer_launch_scan(kp, n_chunks, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(SMG_ERR_CUDA, std::string("scan_kmer_kernel: ") + cudaGetErrorString(e));
+    ++g_launches;
+    return SMG_OK;
+}
+
 int smg_adjudicate(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
                    const smg_row_t* d_rows, const int32_t* d_out_rows, const double* d_thr64, const smg_near_t* d_near,
                    uint64_t near_cap, int pos_bits, int motif_bits, uint64_t* d_hit_keys, float* d_hit_scores, uint64_t hit_cap,
@@ -1131,6 +1157,7 @@ int smg_variant_windows(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t
     if (!s || !d_packed || !d_amask || !d_rows || !d_snv_row || !d_snv_pos || !d_snv_alt || n_snv < 0 || !d_ref_max || !d_alt_max)
         return fail(SMG_ERR_INVALID, "smg_variant_windows: bad argument");
     if (n_snv == 0) return SMG_OK;
+    if (s->kmin > 1) return fail(SMG_ERR_INVALID, "smg_variant_windows: needs a PWM set built without a k-mer split");
     ScanParams p;
     fill_params(p, s, d_packed, d_amask, d_codes, d_rows, nullptr);
     cudaStream_t st = (cudaStream_t)stream;

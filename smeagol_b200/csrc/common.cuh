@@ -91,3 +91,66 @@ struct ScanParams {
     const int32_t* lane_motif;    // [n_groups][SMG_MAX_PWMS_PER_LANE][32], -1 = empty slot
     int32_t first_group;          // first group of the bucket being launched
 };
+
+// ---------------------------------------------------------------------------------- exact window scores (shared)
+// score of one window on the forward string, strand st, fp32 ascending-k order (same order as the register kernel)
+__device__ __forceinline__ float window_score32(const ScanParams& p, const smg_row_t& row, const int motif, const int st, const int64_t s)
+{
+    const int wm = p.motif_width[motif];
+    const float* tab = p.nat_tab + p.motif_off[motif] * 4;
+    float acc = 0.f;
+    for (int k = 0; k < wm; ++k) {
+        const int c = smg_fetch_code(p.packed, p.amask, p.codes, row, s + k);
+        const float* tr = tab + (st ? (wm - 1 - k) : k) * 4;
+        const float t0 = st ? tr[3] : tr[0], t1 = st ? tr[2] : tr[1], t2 = st ? tr[1] : tr[2], t3 = st ? tr[0] : tr[3];
+        const float term = smg_mix(c_emb[c][0], c_emb[c][1], c_emb[c][2], c_emb[c][3], t0, t1, t2, t3);
+        acc = (k == 0) ? term : __fadd_rn(acc, term);
+    }
+    return acc;
+}
+
+// Same value as window_score32 (bit for bit) for a window of plain A/C/G/T bases that lies inside the row, W <= 32:
+// the bases come from three packed words held in registers, one table load + one add per PWM row.  Returns false when
+// the window needs the general path (ambiguity codes, 'Z', end padding, wider PWM).
+__device__ __forceinline__ bool window_score32_acgt(const ScanParams& p, const smg_row_t& row, const int motif, const int st,
+                                                    const int64_t s, float* out)
+{
+    const int wm = p.motif_width[motif];
+    if (wm > 32 || s < 0 || s + wm > row.n_avail) return false;
+    const int64_t w0 = row.word_off + (s >> 4);
+    if ((p.amask[w0] | p.amask[w0 + 1] | p.amask[w0 + 2]) != 0) return false;  // rows are padded: w0 + 2 is allocated
+    const int sh = 2 * (int)(s & 15);
+    const unsigned long long lo = (unsigned long long)p.packed[w0] | ((unsigned long long)p.packed[w0 + 1] << 32);
+    const unsigned long long hi = (unsigned long long)p.packed[w0 + 2];
+    unsigned long long win = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
+    const float* tab = p.nat_tab + p.motif_off[motif] * 4;
+    const int last = 4 * wm - 1;
+    // forward: T[k][b]; reverse complement on the forward string: T[W-1-k][3-b] = flat index (4W-1) - (4k+b).
+    // Ascending k, one rounded add per row: the summation order of the register-table kernel's ACGT path.
+    float acc = 0.f;
+    for (int k = 0; k < wm; ++k) {
+        const int j = 4 * k + (int)(win & 3ull);
+        win >>= 2;
+        const float term = tab[st ? (last - j) : j];
+        acc = (k == 0) ? term : __fadd_rn(acc, term);
+    }
+    *out = acc;
+    return true;
+}
+
+__device__ __forceinline__ double window_score64(const uint32_t* packed, const uint16_t* amask, const uint8_t* codes, const smg_row_t& row,
+                                 const float* tab, const int wm, const int st, const int64_t s, const int64_t sub_pos,
+                                 const int sub_code)
+{
+    double acc = 0.0;
+    for (int k = 0; k < wm; ++k) {
+        int c = smg_fetch_code(packed, amask, codes, row, s + k);
+        if (s + k == sub_pos) c = sub_code;
+        const float* tr = tab + (st ? (wm - 1 - k) : k) * 4;
+        const float t0 = st ? tr[3] : tr[0], t1 = st ? tr[2] : tr[1], t2 = st ? tr[1] : tr[2], t3 = st ? tr[0] : tr[3];
+        const double term = smg_mix64(c, t0, t1, t2, t3);
+        acc = (k == 0) ? term : __dadd_rn(acc, term);
+    }
+    return acc;
+}
+

@@ -1,0 +1,359 @@
+// K-MER INDEX ENGINE for narrow PWMs (smg_kmer_index_build / smg_scan_kmer).
+//
+// A window of a PWM of width W over A/C/G/T has only 4^W possible contents.  For W <= 12 (and a scan long enough to pay
+// for it) the engine therefore scores every k-mer ONCE per call -- in fp32 in the fixed ascending-k order of the
+// register-table kernel, with the near-threshold band adjudicated in fp64 on the spot -- and keeps, per k-mer, the short
+// list of (PWM, strand, score) that are hits (hit density 1e-4 .. 6e-3: the lists are mostly empty).  The scan itself is
+// then OUTPUT-BOUND: per window start one 2W-bit mask of the packed bases per width class, one table lookup, and one
+// list walk that emits finished hits with scores bit-identical to every other engine.  No per-cell arithmetic at all.
+//
+//   index   head[class offset + x]        first entry of k-mer x (or -1); x = sum_k base(p + k) << 2k
+//           entry {col | flags, score, next}   col = motif * 2 + strand; singly linked (built in one pass with atomicExch)
+//   build   one thread = one (W-2)-base prefix x one column tile: the prefix sum is shared by the 16 k-mers that extend it
+//           (same rounding as a sequential sum, since the order is ascending k)
+//   scan    one thread = one window start; a CTA stages its hits in shared memory and appends them to the global hit list
+//           with one atomic per flush; per-(motif, strand) counts in a shared-memory histogram, flushed per chunk
+//   windows that contain an IUPAC code, 'Z' or the end of the row are scored directly (rare generic path).
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kmer.h"
+
+namespace smg {
+
+// ---------------------------------------------------------------------------------------------------- build
+// grid.x: prefixes of (W - tail) bases, 128 per CTA; grid.y: tiles of 16 motifs of the class
+template <int TAIL>
+__global__ void __launch_bounds__(128) kmer_build_kernel(const KmerParams kp, const int W)
+{
+    const ScanParams& p = kp.sp;
+    constexpr int kTile = 16;
+    __shared__ float s_tab[kTile][kKmerMaxW * 4];
+    __shared__ float s_lo[kTile], s_hi[kTile];
+    __shared__ double s_t64[kTile];
+    __shared__ int s_m[kTile];
+    const int c0 = kp.cls_off[W], n_cm = kp.cls_off[W + 1] - c0;
+    const int m0 = blockIdx.y * kTile;
+    const int nt = min(kTile, n_cm - m0);
+    for (int i = threadIdx.x; i < nt * W * 4; i += blockDim.x) {
+        const int t = i / (W * 4), j = i % (W * 4);
+        const int m = kp.cls_motifs[c0 + m0 + t];
+        s_tab[t][j] = p.nat_tab[p.motif_off[m] * 4 + j];
+    }
+    if (threadIdx.x < nt) {
+        const int m = kp.cls_motifs[c0 + m0 + threadIdx.x];
+        s_m[threadIdx.x] = m;
+        s_lo[threadIdx.x] = p.thr_lo[m];
+        s_hi[threadIdx.x] = p.thr_hi[m];
+        s_t64[threadIdx.x] = kp.thr64[m];
+    }
+    __syncthreads();
+    const int pre = W - TAIL;
+    const long long n_pre = 1ll << (2 * pre);
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_pre) return;
+    const int last = 4 * W - 1;
+    int32_t* head = kp.head + kp.head_off[W];
+    for (int t = 0; t < nt; ++t) {
+        const float* tab = s_tab[t];
+        for (int st = 0; st < 2; ++st) {
+            if (!((p.strands >> st) & 1)) continue;
+            // forward: T[k][b] = tab[4k + b]; reverse complement on the forward string: tab[last - (4k + b)]
+            float acc = 0.f;
+            for (int k = 0; k < pre; ++k) {
+                const int j = 4 * k + (int)((q >> (2 * k)) & 3);
+                const float term = tab[st ? (last - j) : j];
+                acc = (k == 0) ? term : __fadd_rn(acc, term);
+            }
+#pragma unroll
+            for (int tl = 0; tl < (1 << (2 * TAIL)); ++tl) {
+                float s = acc;
+#pragma unroll
+                for (int u = 0; u < TAIL; ++u) {
+                    const int k = pre + u;
+                    const int j = 4 * k + ((tl >> (2 * u)) & 3);
+                    const float term = tab[st ? (last - j) : j];
+                    s = (k == 0) ? term : __fadd_rn(s, term);
+                }
+                if (!(s > s_lo[t])) continue;
+                const long long x = q | ((long long)tl << (2 * pre));
+                uint32_t flags = 0;
+                if (!(s > s_hi[t])) {  // near-threshold band: decide in fp64 (same operands, same order)
+                    double a64 = 0.0;
+                    for (int k = 0; k < W; ++k) {
+                        const int j = 4 * k + (int)((x >> (2 * k)) & 3);
+                        const double term = (double)tab[st ? (last - j) : j];
+                        a64 = (k == 0) ? term : __dadd_rn(a64, term);
+                    }
+                    flags = kEntNear | ((a64 > s_t64[t]) ? 0u : kEntRej);
+                }
+                const unsigned long long idx = atomicAdd(&p.counters[SMG_CTR_KMER_ENTRIES], 1ull);
+                if (idx < kp.entry_cap) {
+                    smg_kmer_entry_t e;
+                    e.col = (uint32_t)(s_m[t] * 2 + st) | flags;
+                    e.score = s;
+                    e.next = atomicExch(&head[x], (int32_t)idx);
+                    e.reserved = 0;
+                    kp.entries[idx] = e;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- scan
+struct KmerStage {
+    unsigned long long keys[kKmerStage];
+    float scores[kKmerStage];
+};
+
+// direct scoring of one window that the index cannot serve (IUPAC code, 'Z', end padding): every PWM of the class
+__device__ __noinline__ void kmer_slow_window(const KmerParams& kp, const smg_row_t& row, const int r, const int W, const long long s,
+                                              unsigned long long* s_keys, float* s_scores, int* s_n, int* s_hist, unsigned* tallies)
+{
+    const ScanParams& p = kp.sp;
+    const int key_shift = p.pos_bits + p.motif_bits;
+    const long long smax = row.g_len - row.g_off - (long long)W;
+    for (int i = kp.cls_off[W]; i < kp.cls_off[W + 1]; ++i) {
+        const int m = kp.cls_motifs[i];
+        for (int st = 0; st < 2; ++st) {
+            if (!((p.strands >> st) & 1)) continue;
+            const float v = window_score32(p, row, m, st, s);
+            if (!(v > p.thr_lo[m])) continue;
+            bool hit = true;
+            if (!(v > p.thr_hi[m])) {
+                ++tallies[1];
+                const double s64 = window_score64(p.packed, p.amask, p.codes, row, p.nat_tab + p.motif_off[m] * 4, W, st, s, -1, 0);
+                hit = s64 > kp.thr64[m];
+                if (hit) ++tallies[2];
+            } else {
+                ++tallies[0];
+            }
+            if (!hit) continue;
+            if (s_hist) atomicAdd(&s_hist[m * 2 + st], 1);
+            else if (p.counts) atomicAdd(p.counts + ((size_t)r * p.n_motifs + m) * 2 + st, 1);
+            if (p.hit_keys) {
+                const long long pos = st ? (smax - s) : (row.g_off + s);
+                const unsigned long long key = ((unsigned long long)(unsigned)p.out_rows[r * 2 + st] << key_shift) |
+                                               ((unsigned long long)pos << p.motif_bits) | (unsigned long long)(unsigned)m;
+                const int slot = atomicAdd(s_n, 1);
+                if (slot < kKmerStage) {
+                    s_keys[slot] = key;
+                    s_scores[slot] = v;
+                } else {  // stage full (many generic windows at once): straight to the global list
+                    const unsigned long long gi = atomicAdd(&p.counters[SMG_CTR_HITS_APPENDED], 1ull);
+                    if (gi < p.hit_cap) {
+                        p.hit_keys[gi] = key;
+                        p.hit_scores[gi] = v;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// dynamic shared memory: [2 * n_motifs] int histogram (hist_in_smem) -- counts of this chunk's row
+__global__ void __launch_bounds__(kKmerThreads) scan_kmer_kernel(const KmerParams kp, const int hist_in_smem)
+{
+    const ScanParams& p = kp.sp;
+    extern __shared__ int s_hist_dyn[];
+    __shared__ KmerStage st;
+    __shared__ int s_n;
+    __shared__ unsigned long long s_base;
+    __shared__ unsigned s_tally[3];
+    int* s_hist = hist_in_smem && p.counts ? s_hist_dyn : nullptr;
+    const smg_chunk_t ch = p.chunks[blockIdx.x];
+    const smg_row_t row = p.rows[ch.row];
+    const int c0 = ch.start, c1 = min(c0 + p.chunk_len, row.n_own);
+    if (c1 <= c0) return;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int key_shift = p.pos_bits + p.motif_bits;
+    if (s_hist)
+        for (int i = tid; i < 2 * p.n_motifs; i += kKmerThreads) s_hist[i] = 0;
+    if (tid == 0) s_n = 0;
+    if (tid < 3) s_tally[tid] = 0;
+    __syncthreads();
+    const uint32_t* __restrict__ wp = p.packed + row.word_off;
+    const uint16_t* __restrict__ ap = p.amask + row.word_off;
+    const unsigned long long orow0 = (unsigned long long)(unsigned)p.out_rows[ch.row * 2] << key_shift;
+    const unsigned long long orow1 = (unsigned long long)(unsigned)p.out_rows[ch.row * 2 + 1] << key_shift;
+    unsigned tallies[3] = {0, 0, 0};  // definite, near, accepted
+    unsigned present = 0;
+    for (int W = 1; W <= kp.max_w; ++W)
+        if (kp.cls_off[W + 1] > kp.cls_off[W]) present |= 1u << W;
+
+    auto flush = [&]() {  // all threads
+        __syncthreads();
+        const int n = min(s_n, kKmerStage);
+        if (n > 0 && p.hit_keys) {
+            if (tid == 0) s_base = atomicAdd(&p.counters[SMG_CTR_HITS_APPENDED], (unsigned long long)n);
+            __syncthreads();
+            const unsigned long long base = s_base;
+            for (int i = tid; i < n; i += kKmerThreads)
+                if (base + i < p.hit_cap) {
+                    p.hit_keys[base + i] = st.keys[i];
+                    p.hit_scores[base + i] = st.scores[i];
+                }
+        }
+        __syncthreads();
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+    };
+
+    for (int pb = c0; pb < c1; pb += kKmerThreads) {
+        const int s = pb + tid;
+        const bool active = s < c1;
+        uint32_t win = 0, am = 0xffffu;
+        if (active) {
+            const int w = s >> 4, sh = s & 15;
+            const uint32_t p0 = wp[w], p1 = wp[w + 1];
+            const uint32_t a0 = ap[w], a1 = ap[w + 1];
+            win = __funnelshift_r(p0, p1, 2 * sh);
+            am = ((a0 | (a1 << 16)) >> sh) & 0xffffu;
+        }
+        // ---- every class's list head first (independent loads, one per class), then the list walks.  The class loop is
+        // fully unrolled so that the heads stay in registers; `present` (bit W: the class has PWMs) is CTA-uniform.
+        int heads[kKmerMaxW + 1];
+        unsigned slow = 0;  // bit W: class W needs the generic path here
+#pragma unroll
+        for (int W = 1; W <= kKmerMaxW; ++W) {
+            heads[W] = -1;
+            if (!((present >> W) & 1u) || !active) continue;
+            if ((long long)s > row.g_len - row.g_off - (long long)W) continue;  // models.py:110 trim
+            if (am & ((1u << W) - 1u)) { slow |= 1u << W; continue; }
+            heads[W] = kp.head[kp.head_off[W] + (win & (uint32_t)((1ull << (2 * W)) - 1ull))];
+        }
+#pragma unroll
+        for (int W = 1; W <= kKmerMaxW; ++W) {
+            int e = heads[W];
+            if (e < 0) continue;
+            const long long smax = row.g_len - row.g_off - (long long)W;
+            do {
+                const smg_kmer_entry_t ent = kp.entries[e];
+                e = ent.next;
+                if (ent.col & kEntNear) ++tallies[1];
+                if (ent.col & kEntRej) continue;
+                if (ent.col & kEntNear) ++tallies[2]; else ++tallies[0];
+                const uint32_t col = ent.col & 0x1fffffffu;
+                const int m = (int)(col >> 1), sd = (int)(col & 1u);
+                if (s_hist) atomicAdd(&s_hist[col], 1);
+                else if (p.counts) atomicAdd(p.counts + ((size_t)ch.row * p.n_motifs + m) * 2 + sd, 1);
+                if (p.hit_keys) {
+                    const long long pos = sd ? (smax - s) : (row.g_off + s);
+                    const unsigned long long key = (sd ? orow1 : orow0) | ((unsigned long long)pos << p.motif_bits) |
+                                                   (unsigned long long)(unsigned)m;
+                    const int slot = atomicAdd(&s_n, 1);  // same address for the whole warp: the compiler aggregates it
+                    if (slot < kKmerStage) {
+                        st.keys[slot] = key;
+                        st.scores[slot] = ent.score;
+                    } else {  // stage full: straight to the global list (rare: the stage is flushed when half full)
+                        const unsigned long long gi = atomicAdd(&p.counters[SMG_CTR_HITS_APPENDED], 1ull);
+                        if (gi < p.hit_cap) {
+                            p.hit_keys[gi] = key;
+                            p.hit_scores[gi] = ent.score;
+                        }
+                    }
+                }
+            } while (e >= 0);
+        }
+        // ---- generic path for windows the index cannot serve
+        if (__syncthreads_or(slow != 0u)) {
+            flush();  // the slow path appends through s_n one hit at a time: start from an empty stage
+            if (slow) {
+                for (int W = 1; W <= kp.max_w; ++W)
+                    if ((slow >> W) & 1u) {
+                        // keep the stage from overflowing: at most 2 * class size hits per window
+                        kmer_slow_window(kp, row, ch.row, W, s, st.keys, st.scores, &s_n, s_hist, tallies);
+                    }
+            }
+            flush();
+        } else if (s_n > kKmerStage / 2) {
+            flush();
+        }
+    }
+    flush();
+    if (s_hist && p.counts) {
+        for (int i = tid; i < 2 * p.n_motifs; i += kKmerThreads) {
+            const int v = s_hist[i];
+            if (v) atomicAdd(p.counts + (size_t)ch.row * p.n_motifs * 2 + i, v);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) tallies[i] = __reduce_add_sync(SMG_FULL_MASK, tallies[i]);
+    if (lane == 0) {
+        if (tallies[0]) atomicAdd(&s_tally[0], tallies[0]);
+        if (tallies[1]) atomicAdd(&s_tally[1], tallies[1]);
+        if (tallies[2]) atomicAdd(&s_tally[2], tallies[2]);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (s_tally[0]) atomicAdd(&p.counters[SMG_CTR_DEFINITE], (unsigned long long)s_tally[0]);
+        if (s_tally[1]) atomicAdd(&p.counters[SMG_CTR_NEAR_TC], (unsigned long long)s_tally[1]);
+        if (s_tally[2]) atomicAdd(&p.counters[SMG_CTR_ADJ_ACCEPTED], (unsigned long long)s_tally[2]);
+    }
+}
+
+}  // namespace smg
+
+// ---------------------------------------------------------------------------------------------------- host side
+int smg_kmer_fill_params(smg::KmerParams& kp, const std::vector<int>& widths, const int32_t* d_cls_motifs, int max_w)
+{
+    if (max_w < 1 || max_w > smg::kKmerMaxW) return 1;
+    kp.cls_motifs = d_cls_motifs;
+    kp.max_w = max_w;
+    int off = 0;
+    int64_t hoff = 0;
+    for (int W = 0; W <= smg::kKmerMaxW + 1; ++W) {
+        kp.cls_off[W] = off;
+        kp.head_off[W] = hoff;
+        if (W >= 1 && W <= smg::kKmerMaxW) {
+            int n = 0;
+            for (int w : widths) n += (w == W);
+            off += n;
+            if (n > 0 && W <= max_w) hoff += 1ll << (2 * W);
+        }
+    }
+    return 0;
+}
+
+int64_t smg_kmer_head_len(const std::vector<int>& widths, int max_w)
+{
+    int64_t h = 0;
+    for (int W = 1; W <= std::min(max_w, smg::kKmerMaxW); ++W) {
+        bool any = false;
+        for (int w : widths) any = any || (w == W);
+        if (any) h += 1ll << (2 * W);
+    }
+    return h;
+}
+
+cudaError_t smg_kmer_launch_build(const smg::KmerParams& kp, cudaStream_t st, uint64_t* n_launches)
+{
+    for (int W = 1; W <= kp.max_w; ++W) {
+        const int n_cm = kp.cls_off[W + 1] - kp.cls_off[W];
+        if (n_cm == 0) continue;
+        const int tail = std::min(W, 2);
+        const long long n_pre = 1ll << (2 * (W - tail));
+        dim3 grid((unsigned)((n_pre + 127) / 128), (unsigned)((n_cm + 15) / 16), 1);
+        if (tail == 2) smg::kmer_build_kernel<2><<<grid, 128, 0, st>>>(kp, W);
+        else smg::kmer_build_kernel<1><<<grid, 128, 0, st>>>(kp, W);
+        ++*n_launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t smg_kmer_launch_scan(const smg::KmerParams& kp, int n_chunks, cudaStream_t st)
+{
+    const size_t hist_bytes = (size_t)kp.sp.n_motifs * 2 * sizeof(int);
+    const int in_smem = hist_bytes <= 96 * 1024;
+    if (in_smem && hist_bytes > 8 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(smg::scan_kmer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes);
+        if (e != cudaSuccess) return e;
+    }
+    smg::scan_kmer_kernel<<<(unsigned)n_chunks, smg::kKmerThreads, in_smem ? hist_bytes : 0, st>>>(kp, in_smem);
+    return cudaGetLastError();
+}

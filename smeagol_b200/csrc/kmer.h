@@ -1,0 +1,34 @@
+// Host-side interface of the k-mer index engine (kmer.cu), used by the C-ABI entry points in api.cu.
+#pragma once
+#include <cstdint>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace smg {
+
+constexpr int kKmerMaxW = 12;
+constexpr int kKmerStage = 2048;         // hits staged per CTA before a flush
+constexpr int kKmerThreads = 256;
+constexpr uint32_t kEntNear = 1u << 30;  // decided by the fp64 adjudicator
+constexpr uint32_t kEntRej = 1u << 29;   // inside the band, rejected in fp64 (kept so that the scan can count it)
+
+struct KmerParams {
+    ScanParams sp;
+    const int32_t* cls_motifs;        // motif ids sorted by width
+    int32_t cls_off[kKmerMaxW + 2];   // class W = motifs cls_motifs[cls_off[W] .. cls_off[W + 1])
+    int64_t head_off[kKmerMaxW + 2];  // first head slot of class W
+    int32_t max_w;                    // classes 1 .. max_w
+    int32_t* head;
+    smg_kmer_entry_t* entries;
+    unsigned long long entry_cap;
+    const double* thr64;
+};
+
+}  // namespace smg
+
+int smg_kmer_fill_params(smg::KmerParams& kp, const std::vector<int>& widths, const int32_t* d_cls_motifs, int max_w);
+int64_t smg_kmer_head_len(const std::vector<int>& widths, int max_w);
+cudaError_t smg_kmer_launch_build(const smg::KmerParams& kp, cudaStream_t st, uint64_t* n_launches);
+cudaError_t smg_kmer_launch_scan(const smg::KmerParams& kp, int n_chunks, cudaStream_t st);

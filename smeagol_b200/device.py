@@ -19,7 +19,10 @@ ROW_PAD_BASES = 96  # every row is followed by at least this many 'Z' bases (hal
 NEAR_REL = 1e-5     # half-width of the near-threshold band, relative to sum_k max_b |T[k,b]|
 STRANDS = {"none": 1, "only": 2, "both": 3}
 DEFAULT_ENGINE = "regtab"
-DEFAULT_TC_KIND = "tc5"  # tensor-core prefilter of the 'auto' / tensor-core engines: 'hmma' (mma.sync) or 'tc5' (tcgen05 + TMEM)
+DEFAULT_TC_KIND = "tc5"
+KMER_MAX_WIDTH = 12   # widest class of the k-mer index engine (csrc/kmer.cu)
+KMER_ALPHA = 1.0      # a width class W joins the k-mer index when 4^W <= KMER_ALPHA * (window starts of the scan): scoring all
+                      # k-mers once costs about as much per (k-mer, PWM) as any engine spends per (position, PWM)  # tensor-core prefilter of the 'auto' / tensor-core engines: 'hmma' (mma.sync) or 'tc5' (tcgen05 + TMEM)
 DEFAULT_TC_MIN_WIDTH = 7  # measured per width (profiles/r01_bench_widths.txt): the register-table engine wins up to W = 6 (hit density >= 6e-3 at thr 0.7), the tensor-core prefilter from W = 7
 
 
@@ -145,28 +148,37 @@ class DevicePWMSet:
     """Device tables of a PWM library (models.py:70-90 pads PWMs into one Conv1D kernel; here: natural fp32 tables,
     reverse-complement tables and lane-major register-table groups, built by smg_pwmset_create)."""
 
-    def __init__(self, weights, device=None, tc_min_width=None):
-        """Non-finite weights (log2 of a zero probability) are accepted as in the reference, where such a PWM never yields
+    def __init__(self, weights, device=None, tc_min_width=None, kmer_max_width=0):
+        """kmer_max_width > 0: PWMs up to that width are left to the k-mer index engine (they are in no lane group or
+        tensor-core table of this set; ScanPlan asks for such a sibling through with_kmer()).
+        Non-finite weights (log2 of a zero probability) are accepted as in the reference, where such a PWM never yields
         a site (ScanPlan switches it off).  tc_min_width: PWMs at least this wide go to the tensor-core engine, narrower ones to the
         register-table engine (engine 'auto'); 0 = no split (either engine alone covers every PWM)."""
         self.device = _require_cuda(device)
         if tc_min_width is None:
             tc_min_width = int(os.environ.get("SMEAGOL_B200_TC_MIN_WIDTH", DEFAULT_TC_MIN_WIDTH))
         self.tc_min_width = int(tc_min_width)
+        self.kmer_max_width = int(kmer_max_width) if self.tc_min_width > 0 else 0
+        self._siblings = {}
         lib = _lib.load()
         w32 = [np.ascontiguousarray(np.asarray(w), dtype=np.float32) for w in weights]
+        self._w32 = w32
         for w in w32:
             if w.ndim != 2 or w.shape[1] != 4:
                 raise ValueError("PWM weights must have shape (W, 4)")
         self.n_motifs = len(w32)
         self.widths = np.array([w.shape[0] for w in w32], dtype=np.int32)
         flat = np.concatenate([w.reshape(-1) for w in w32]).astype(np.float32)
+        if np.any(np.isfinite(flat) & (np.abs(flat) > 6e4)):
+            self.tc_min_width = self.kmer_max_width = 0  # fp16 prefilter tables cannot hold such weights: FP32 engine only
         self.abs_scale = np.array([np.abs(w.astype(np.float64)).max(axis=1).sum() for w in w32])
         handle = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            _lib.check(lib.smg_pwmset_create_split(flat.ctypes.data_as(ctypes.c_void_p),
-                                                   self.widths.ctypes.data_as(ctypes.c_void_p), self.n_motifs,
-                                                   self.tc_min_width, ctypes.byref(handle)), "smg_pwmset_create_split")
+            kmin = self.kmer_max_width + 1 if self.kmer_max_width > 0 else 0
+            _lib.check(lib.smg_pwmset_create_split3(flat.ctypes.data_as(ctypes.c_void_p),
+                                                    self.widths.ctypes.data_as(ctypes.c_void_p), self.n_motifs, kmin,
+                                                    max(self.tc_min_width, kmin) if self.tc_min_width > 0 else 0,
+                                                    ctypes.byref(handle)), "smg_pwmset_create_split3")
         self.handle = handle
         info = (ctypes.c_int64 * 8)()
         _lib.check(lib.smg_pwmset_info(handle, info), "smg_pwmset_info")
@@ -176,7 +188,19 @@ class DevicePWMSet:
         self.n_wide = int(info[4])
         self.sum_padded_width = int(info[5])
 
+    def with_kmer(self, kmer_max_width):
+        """Sibling set whose PWMs up to kmer_max_width are left to the k-mer index engine (built once, cached)."""
+        if kmer_max_width == self.kmer_max_width:
+            return self
+        if kmer_max_width not in self._siblings:
+            self._siblings[kmer_max_width] = DevicePWMSet(self._w32, device=self.device, tc_min_width=self.tc_min_width,
+                                                          kmer_max_width=kmer_max_width)
+        return self._siblings[kmer_max_width]
+
     def close(self):
+        for sib in getattr(self, "_siblings", {}).values():
+            sib.close()
+        self._siblings = {}
         if getattr(self, "handle", None):
             _lib.load().smg_pwmset_destroy(self.handle)
             self.handle = None
@@ -286,6 +310,20 @@ class ScanPlan:
             self.engine = "auto"    # the PWM set was built split: both engines run, each on its side
         elif self.engine == "auto" or (self.engine == "hmma" and pwmset.n_wide > 0):
             self.engine = "regtab"  # PWMs wider than 32 only exist in the register-table / generic path
+        # ---- k-mer index engine for the narrow width classes (engine 'auto' only)
+        self.kmer_w = 0
+        if self.engine == "auto" and os.environ.get("SMEAGOL_B200_KMER", "1") != "0":
+            forced = os.environ.get("SMEAGOL_B200_KMER_MAX_WIDTH")
+            wk = 0
+            for w in range(1, KMER_MAX_WIDTH + 1):
+                if 4 ** w <= KMER_ALPHA * max(batch.total_own, 1):
+                    wk = w
+            if forced is not None:
+                wk = max(0, min(KMER_MAX_WIDTH, int(forced)))
+            present = np.unique(pwmset.widths)
+            present = present[present <= wk]
+            self.kmer_w = int(present.max()) if present.size else 0
+            pwmset = pwmset.with_kmer(self.kmer_w)
         self.pwmset, self.batch = pwmset, batch
         dev = batch.device
         M = pwmset.n_motifs
@@ -334,6 +372,43 @@ class ScanPlan:
             # tc5: every epilogue warp of every CTA keeps two blocks of 128 candidate slots reserved
             self.cand_cap = int(self.hit_cap * 1.25) + 4096 + ((1 << 20) if self.tc_kind == "tc5" else 0)
         self._alloc()
+        if self.kmer_w > 0:
+            self._build_kmer_index()
+
+    def _build_kmer_index(self):
+        """Score every k-mer of the narrow width classes once for this plan's thresholds (csrc/kmer.cu)."""
+        dev, lib = self.batch.device, self.lib
+        hl = ctypes.c_int64(0)
+        _lib.check(lib.smg_kmer_index_size(self.pwmset.handle, self.kmer_w, ctypes.byref(hl)), "smg_kmer_index_size")
+        self.kmer_head = torch.empty(max(int(hl.value), 1), dtype=torch.int32, device=dev)
+        w = self.pwmset.widths.astype(np.int64)
+        est = int(sum(4.0 ** int(x) * 2 * 3e-3 for x in w[w <= self.kmer_w]))
+        cap = max(1 << 16, min(est, 1 << 26))
+        ctr = torch.zeros(_lib.N_COUNTERS, dtype=torch.int64, device=dev)
+        while True:
+            self.kmer_entries = torch.empty(cap * 16, dtype=torch.uint8, device=dev)
+            ctr.zero_()
+            _lib.check(lib.smg_kmer_index_build(self.pwmset.handle, self.kmer_w, self.strands, _ptr(self.d_lo), _ptr(self.d_hi),
+                                                _ptr(self.d_thr), _ptr(self.kmer_head), int(hl.value), _ptr(self.kmer_entries), cap,
+                                                _ptr(ctr), _stream()), "smg_kmer_index_build")
+            need = int(ctr[_lib.CTR_KMER_ENTRIES].item())
+            if need <= cap:
+                break
+            if need >= (1 << 31) - 1:
+                raise _lib.SmeagolB200Error("k-mer index too large (threshold too low for the k-mer engine)")
+            cap = min(int(need * 1.1) + 1024, (1 << 31) - 2)
+        self.kmer_cap, self.kmer_n_entries = cap, need
+
+    def launch_kmer_side(self):
+        """K-mer index engine on the width classes up to kmer_w (hits, counts and tallies like the other engines)."""
+        if self.kmer_w <= 0:
+            return
+        b, lib = self.batch, self.lib
+        _lib.check(lib.smg_scan_kmer(self.pwmset.handle, self.kmer_w, _ptr(b.packed), _ptr(b.amask), _ptr(b.codes), _ptr(b.d_rows),
+                                     b.n_rows, _ptr(self.d_out_rows), _ptr(self.d_chunks), self.n_chunks, self.chunk_len,
+                                     self.strands, _ptr(self.d_lo), _ptr(self.d_hi), _ptr(self.d_thr), self.pos_bits, self.motif_bits,
+                                     _ptr(self.kmer_head), _ptr(self.kmer_entries), self.kmer_cap, _ptr(self.keys), _ptr(self.scores),
+                                     self.hit_cap, _ptr(self.counts), _ptr(self.counters), _stream()), "smg_scan_kmer")
 
     def _alloc(self):
         dev = self.batch.device
@@ -356,10 +431,9 @@ class ScanPlan:
 
     def launch_scan(self):
         """Enqueue the scan kernels only (the tensor-core engine's exact second pass includes the adjudication)."""
-        if self.engine == "auto":  # register-table side (+ its adjudication), then the tensor-core side
-            self._launch_regtab()
-            if self.adjudicate:
-                self.launch_adjudicate()
+        if self.engine == "auto":  # k-mer index side, register-table side (+ its adjudication), then the tensor-core side
+            self.launch_kmer_side()
+            self.launch_regtab_side()
         if self.engine in ("hmma", "auto"):
             self.launch_tc_side()
             return
@@ -367,6 +441,8 @@ class ScanPlan:
 
     def launch_regtab_side(self):
         """Register-table engine on its side of the width split, with its fp64 adjudication (engine 'auto')."""
+        if self.pwmset.n_groups == 0 and self.pwmset.n_wide == 0:
+            return  # every narrow PWM is served by the k-mer index
         self._launch_regtab()
         if self.adjudicate:
             self.launch_adjudicate()
@@ -420,7 +496,8 @@ class ScanPlan:
                  "n_adjudicated_accepted": int(c[_lib.CTR_ADJ_ACCEPTED]),
                  "n_hits_total": int(c[_lib.CTR_DEFINITE]) + int(c[_lib.CTR_ADJ_ACCEPTED]), "chunk_len": self.chunk_len,
                  "n_chunks": self.n_chunks, "hit_cap": self.hit_cap, "near_cap": self.near_cap, "engine": self.engine,
-                 "tc_kind": self.tc_kind if self.engine in ("hmma", "auto") else None,
+                 "tc_kind": self.tc_kind if self.engine in ("hmma", "auto") else None, "kmer_max_width": self.kmer_w,
+                 "kmer_index_entries": getattr(self, "kmer_n_entries", 0),
                  "n_candidates": int(c[_lib.CTR_CANDIDATES])}
         keys, scores = self.keys, self.scores
         if self.want_hits and sort and n_hits > 0:

@@ -499,6 +499,57 @@ def test_hybrid_engine_split_bit_identical():
     assert res.stats["engine"] == "regtab"
 
 
+def test_kmer_index_engine_bit_identical(monkeypatch):
+    """K-mer index engine (csrc/kmer.cu): every k-mer of the width classes up to 12 scored once per call, hits emitted by
+    table lookup -- identical hits, fp32 scores (bit for bit), counts and near-threshold tallies as the oracle.  Covers
+    every width class 1..12 (+ wider PWMs on the other engines of the same scan), IUPAC / 'Z' windows (generic path),
+    all strand modes, rows ending inside a window, thresholds at both ends, and a forced class limit below a width that
+    is present."""
+    sb = _sb()
+    rng = np.random.default_rng(53)
+    ws = []
+    for W in list(range(1, 15)) * 3:
+        ppm = (rng.dirichlet([0.5] * 4, size=W) + 0.01) / 1.04
+        ws.append(np.log2(ppm / 0.25))
+    df = pd.DataFrame({"Matrix_id": ["W%02d_%d" % (w.shape[0], i) for i, w in enumerate(ws)], "weights": ws})
+    amb = "ACGTNWSMKRYBDHVZ"
+    pa = np.array([0.23] * 4 + [0.08 / 12] * 12)
+    seqs = [rand_seq(rng, 6000), rand_seq(rng, 1500, amb, pa / pa.sum()), rand_seq(rng, 31), "ACGTA", "",
+            "N" * 40 + rand_seq(rng, 300) + "N" * 40]
+    for wk in ("12", "7", "3"):
+        monkeypatch.setenv("SMEAGOL_B200_KMER_MAX_WIDTH", wk)
+        model = sb.models.PWMModel(df)  # default split: engine 'auto' = k-mer index + register tables + tensor cores
+        res, exp = check_against_oracle(model, seqs, 0.6, "both", chunk_len=512)
+        assert res.stats["engine"] == "auto" and res.stats["kmer_max_width"] == int(wk)
+        assert res.stats["kmer_index_entries"] > 0
+        check_against_oracle(model, seqs, 0.6, "none")
+        check_against_oracle(model, seqs, 0.6, "only", chunk_len=4096)
+    monkeypatch.setenv("SMEAGOL_B200_KMER_MAX_WIDTH", "10")
+    model = sb.models.PWMModel(df)
+    check_against_oracle(model, seqs, 1.0, "both")
+    check_against_oracle(model, [rand_seq(rng, 2000)], 0.15, "both", atol=1e-5)  # dense lists: many entries per k-mer
+    # segments with halo: ownership and reverse-complement coordinates come from the row descriptor
+    whole = rand_seq(rng, 5000)
+    res_w = device_scan(model, [whole], 0.6)
+    L, halo = len(whole), model.max_width - 1
+    cuts = [0, 1600, 3328, L]
+    parts = [whole[a:min(L, b + halo)] for a, b in zip(cuts[:-1], cuts[1:])]
+    segs = [(a, L, b - a) for a, b in zip(cuts[:-1], cuts[1:])]
+    from smeagol_b200 import device as dev
+
+    batch = dev.SeqBatch(parts, segments=segs)
+    out_rows = np.array([[0, 1]] * 3, dtype=np.int32)
+    res_s = dev.scan(model.device_set, batch, model.thresholds(0.6), 3, out_rows, 2)
+    a, b = res_w.hits_host(), res_s.hits_host()
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
+    monkeypatch.delenv("SMEAGOL_B200_KMER_MAX_WIDTH")
+    # automatic choice: 4^W <= window starts of the scan
+    model = sb.models.PWMModel(df)
+    res, _ = check_against_oracle(model, [rand_seq(rng, 70000)], 0.7, "both")
+    assert res.stats["kmer_max_width"] == 8
+
+
 @pytest.mark.gpu
 def test_nonfinite_weights_never_hit_like_the_reference():
     """log2 of a zero probability gives -inf weights.  The reference contracts the full one-hot vector with every
