@@ -1030,7 +1030,10 @@ int smg_kmer_index_build(smg_pwmset_t s, int kmer_max_width, int strands, const 
     kp.sp.counters = reinterpret_cast<unsigned long long*>(d_counters);
     if (smg_kmer_fill_params(kp, s->widths, s->d_cls_motifs, kmer_max_width)) return fail(SMG_ERR_INVALID, "smg_kmer_index_build: bad width");
     kp.head = d_head; kp.entries = d_entries; kp.entry_cap = entry_cap; kp.thr64 = d_thr64;
-    SMG_CUDA(cudaMemsetAsync(d_head, 0xff, (size_t)head_len * sizeof(int32_t), st));
+    int64_t n_heads = 0;
+    smg_kmer_head_len(s->widths, kmer_max_width, &n_heads);
+    SMG_CUDA(cudaMemsetAsync(d_head, 0xff, (size_t)n_heads * sizeof(int32_t), st));                         // empty lists
+    SMG_CUDA(cudaMemsetAsync(d_head + n_heads, 0, (size_t)(head_len - n_heads) * sizeof(int32_t), st));   // bitmaps
     uint64_t nl = 0;
     cudaError_t e = smg_kmer_launch_build(kp, st, &nl);
     g_launches += nl;

@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(128) kmer_build_kernel(const KmerParams kp, co
                     e.col = (uint32_t)(s_m[t] * 2 + st) | flags;
                     e.score = s;
                     e.next = atomicExch(&head[x], (int32_t)idx);
+                    atomicOr(reinterpret_cast<unsigned*>(kp.head + kp.bm_off[W]) + (x >> 5), 1u << (x & 31));
                     e.reserved = 0;
                     kp.entries[idx] = e;
                 }
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(kKmerThreads) scan_kmer_kernel(const KmerParam
     const ScanParams& p = kp.sp;
     extern __shared__ int s_hist_dyn[];
     __shared__ KmerStage st;
+    __shared__ int2 s_wq[kKmerThreads / 32][32 * kKmerMaxW];  // per-warp work queue: at most one item per (lane, class)
     __shared__ int s_n;
     __shared__ unsigned long long s_base;
     __shared__ unsigned s_tally[3];
@@ -169,6 +171,8 @@ __global__ void __launch_bounds__(kKmerThreads) scan_kmer_kernel(const KmerParam
     const int c0 = ch.start, c1 = min(c0 + p.chunk_len, row.n_own);
     if (c1 <= c0) return;
     const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int2* wq = s_wq[tid >> 5];
     const int key_shift = p.pos_bits + p.motif_bits;
     if (s_hist)
         for (int i = tid; i < 2 * p.n_motifs; i += kKmerThreads) s_hist[i] = 0;
@@ -213,23 +217,49 @@ __global__ void __launch_bounds__(kKmerThreads) scan_kmer_kernel(const KmerParam
             win = __funnelshift_r(p0, p1, 2 * sh);
             am = ((a0 | (a1 << 16)) >> sh) & 0xffffu;
         }
-        // ---- every class's list head first (independent loads, one per class), then the list walks.  The class loop is
-        // fully unrolled so that the heads stay in registers; `present` (bit W: the class has PWMs) is CTA-uniform.
-        int heads[kKmerMaxW + 1];
+        // ---- class lookups: one bitmap probe (wide classes: 95 % of the k-mers have no entry, and the 1-bit tables stay
+        // cache resident while the head tables do not) and one head load per class; the class loop is fully unrolled,
+        // `present` (bit W: the class has PWMs) is CTA-uniform.  Non-empty lists become work items of the warp's queue.
         unsigned slow = 0;  // bit W: class W needs the generic path here
+        unsigned probe = 0; // bit W: class W has a list here
+        uint32_t bmw[kKmerMaxW + 1];
 #pragma unroll
         for (int W = 1; W <= kKmerMaxW; ++W) {
-            heads[W] = -1;
+            bmw[W] = 0;
             if (!((present >> W) & 1u) || !active) continue;
             if ((long long)s > row.g_len - row.g_off - (long long)W) continue;  // models.py:110 trim
             if (am & ((1u << W) - 1u)) { slow |= 1u << W; continue; }
-            heads[W] = kp.head[kp.head_off[W] + (win & (uint32_t)((1ull << (2 * W)) - 1ull))];
+            if (W >= kKmerBitmapMinW) {
+                const uint32_t x = win & (uint32_t)((1ull << (2 * W)) - 1ull);
+                bmw[W] = reinterpret_cast<const uint32_t*>(kp.head + kp.bm_off[W])[x >> 5] >> (x & 31);
+            } else {
+                bmw[W] = 1u;
+            }
         }
+        int heads[kKmerMaxW + 1];
 #pragma unroll
         for (int W = 1; W <= kKmerMaxW; ++W) {
-            int e = heads[W];
-            if (e < 0) continue;
+            heads[W] = -1;
+            if (bmw[W] & 1u) heads[W] = kp.head[kp.head_off[W] + (win & (uint32_t)((1ull << (2 * W)) - 1ull))];
+        }
+        // queue the non-empty lists: item = {entry index, (lane << 4) | W}; ballot + prefix popcount, no atomics
+        int qn = 0;
+#pragma unroll
+        for (int W = 1; W <= kKmerMaxW; ++W) {
+            if (!((present >> W) & 1u)) continue;
+            const bool has = heads[W] >= 0;
+            const unsigned bm = __ballot_sync(SMG_FULL_MASK, has);
+            if (has) wq[qn + __popc(bm & lt_mask)] = make_int2(heads[W], (lane << 4) | W);
+            qn += __popc(bm);
+        }
+        __syncwarp();
+        // ---- list walks with every lane busy: lane i takes item i, i + 32, ...
+        for (int qi = lane; qi < qn; qi += 32) {
+            const int2 item = wq[qi];
+            const int W = item.y & 15;
+            const int sp = pb + (tid & ~31) + (item.y >> 4);  // window start of the item
             const long long smax = row.g_len - row.g_off - (long long)W;
+            int e = item.x;
             do {
                 const smg_kmer_entry_t ent = kp.entries[e];
                 e = ent.next;
@@ -241,7 +271,7 @@ __global__ void __launch_bounds__(kKmerThreads) scan_kmer_kernel(const KmerParam
                 if (s_hist) atomicAdd(&s_hist[col], 1);
                 else if (p.counts) atomicAdd(p.counts + ((size_t)ch.row * p.n_motifs + m) * 2 + sd, 1);
                 if (p.hit_keys) {
-                    const long long pos = sd ? (smax - s) : (row.g_off + s);
+                    const long long pos = sd ? (smax - sp) : (row.g_off + sp);
                     const unsigned long long key = (sd ? orow1 : orow0) | ((unsigned long long)pos << p.motif_bits) |
                                                    (unsigned long long)(unsigned)m;
                     const int slot = atomicAdd(&s_n, 1);  // same address for the whole warp: the compiler aggregates it
@@ -258,6 +288,7 @@ __global__ void __launch_bounds__(kKmerThreads) scan_kmer_kernel(const KmerParam
                 }
             } while (e >= 0);
         }
+        __syncwarp();
         // ---- generic path for windows the index cannot serve
         if (__syncthreads_or(slow != 0u)) {
             flush();  // the slow path appends through s_n one hit at a time: start from an empty stage
@@ -315,18 +346,26 @@ int smg_kmer_fill_params(smg::KmerParams& kp, const std::vector<int>& widths, co
             if (n > 0 && W <= max_w) hoff += 1ll << (2 * W);
         }
     }
+    for (int W = 0; W <= smg::kKmerMaxW + 1; ++W) {  // bitmaps (one bit per k-mer, at least one word) follow the heads
+        kp.bm_off[W] = hoff;
+        if (W >= 1 && W <= max_w && kp.cls_off[W + 1] > kp.cls_off[W]) hoff += std::max<int64_t>(1, (1ll << (2 * W)) >> 5);
+    }
     return 0;
 }
 
-int64_t smg_kmer_head_len(const std::vector<int>& widths, int max_w)
+int64_t smg_kmer_head_len(const std::vector<int>& widths, int max_w, int64_t* n_heads)
 {
-    int64_t h = 0;
+    int64_t h = 0, b = 0;
     for (int W = 1; W <= std::min(max_w, smg::kKmerMaxW); ++W) {
         bool any = false;
         for (int w : widths) any = any || (w == W);
-        if (any) h += 1ll << (2 * W);
+        if (any) {
+            h += 1ll << (2 * W);
+            b += std::max<int64_t>(1, (1ll << (2 * W)) >> 5);
+        }
     }
-    return h;
+    if (n_heads) *n_heads = h;
+    return h ? h + b : 0;
 }
 
 cudaError_t smg_kmer_launch_build(const smg::KmerParams& kp, cudaStream_t st, uint64_t* n_launches)

@@ -9,7 +9,8 @@
 namespace smg {
 
 constexpr int kKmerMaxW = 12;
-constexpr int kKmerStage = 2048;         // hits staged per CTA before a flush
+constexpr int kKmerStage = 1024;         // hits staged per CTA before a flush
+constexpr int kKmerBitmapMinW = 9;       // classes at least this wide are looked up through a 1-bit-per-k-mer bitmap first
 constexpr int kKmerThreads = 256;
 constexpr uint32_t kEntNear = 1u << 30;  // decided by the fp64 adjudicator
 constexpr uint32_t kEntRej = 1u << 29;   // inside the band, rejected in fp64 (kept so that the scan can count it)
@@ -19,6 +20,7 @@ struct KmerParams {
     const int32_t* cls_motifs;        // motif ids sorted by width
     int32_t cls_off[kKmerMaxW + 2];   // class W = motifs cls_motifs[cls_off[W] .. cls_off[W + 1])
     int64_t head_off[kKmerMaxW + 2];  // first head slot of class W
+    int64_t bm_off[kKmerMaxW + 2];    // first bitmap word of class W (in the same int32 buffer, after all heads)
     int32_t max_w;                    // classes 1 .. max_w
     int32_t* head;
     smg_kmer_entry_t* entries;
@@ -29,6 +31,7 @@ struct KmerParams {
 }  // namespace smg
 
 int smg_kmer_fill_params(smg::KmerParams& kp, const std::vector<int>& widths, const int32_t* d_cls_motifs, int max_w);
-int64_t smg_kmer_head_len(const std::vector<int>& widths, int max_w);
+// int32 slots of the index buffer: list heads of every class, then the bitmaps; *n_heads = the head part
+int64_t smg_kmer_head_len(const std::vector<int>& widths, int max_w, int64_t* n_heads = nullptr);
 cudaError_t smg_kmer_launch_build(const smg::KmerParams& kp, cudaStream_t st, uint64_t* n_launches);
 cudaError_t smg_kmer_launch_scan(const smg::KmerParams& kp, int n_chunks, cudaStream_t st);
