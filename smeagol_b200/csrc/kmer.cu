@@ -96,6 +96,15 @@ __global__ void __launch_bounds__(128) kmer_build_kernel(const KmerParams kp, co
                     e.score = s;
                     e.next = atomicExch(&head[x], (int32_t)idx);
                     atomicOr(reinterpret_cast<unsigned*>(kp.head + kp.bm_off[W]) + (x >> 5), 1u << (x & 31));
+                    if (W >= kKmerBitmapMinW && kp.max_w > kKmerBitmapMinW) {
+                        // combined bitmap of the wide classes, keyed by the max_w-mer: every extension of this k-mer
+                        unsigned* cb = reinterpret_cast<unsigned*>(kp.head + kp.cb_off);
+                        const long long n_ext = 1ll << (2 * (kp.max_w - W));
+                        for (long long t2 = 0; t2 < n_ext; ++t2) {
+                            const long long y = x | (t2 << (2 * W));
+                            atomicOr(cb + (y >> 5), 1u << (y & 31));
+                        }
+                    }
                     e.reserved = 0;
                     kp.entries[idx] = e;
                 }
@@ -105,14 +114,67 @@ __global__ void __launch_bounds__(128) kmer_build_kernel(const KmerParams kp, co
 }
 
 // ---------------------------------------------------------------------------------------------------- scan
-struct KmerStage {
-    unsigned long long keys[kKmerStage];
-    float scores[kKmerStage];
+// Per-warp hit stage, double buffered: when a buffer is full its slots in the global hit list are reserved (one atomic,
+// result not awaited), the warp goes on filling the other buffer, and the first one is copied out when the warp next
+// switches -- by then the atomic has long returned.  Warps never wait for one another inside a chunk.
+struct KmerWarpStage {
+    unsigned long long keys[2][kKmerStage];
+    float scores[2][kKmerStage];
+    int n;  // fill of the active buffer
 };
+
+struct KmerEmit {  // per-thread view of its warp's stage (registers)
+    KmerWarpStage* st;
+    int cur;                       // active buffer
+    int pend_n;                    // hits of the other buffer awaiting copy-out (0: none)
+    unsigned long long pend_base;  // their first slot in the global list (valid in lane 0 until broadcast)
+};
+
+__device__ __forceinline__ void kmer_push(const ScanParams& p, KmerEmit& em, const unsigned long long key, const float score)
+{
+    const int slot = atomicAdd(&em.st->n, 1);  // one address per warp: aggregated by the compiler
+    if (slot < kKmerStage) {
+        em.st->keys[em.cur][slot] = key;
+        em.st->scores[em.cur][slot] = score;
+    } else {  // buffer full: straight to the global list (the warp switches buffers when one is half full, so this is rare)
+        const unsigned long long gi = atomicAdd(&p.counters[SMG_CTR_HITS_APPENDED], 1ull);
+        if (gi < p.hit_cap) {
+            p.hit_keys[gi] = key;
+            p.hit_scores[gi] = score;
+        }
+    }
+}
+
+// copy out the pending buffer (if any), then make the active buffer pending (reserve its slots) and switch.  Converged warp.
+__device__ __forceinline__ void kmer_switch(const ScanParams& p, KmerEmit& em, const int lane)
+{
+    __syncwarp();
+    if (em.pend_n > 0) {
+        const unsigned long long base = __shfl_sync(SMG_FULL_MASK, em.pend_base, 0);
+        const int ob = em.cur ^ 1;
+        for (int i = lane; i < em.pend_n; i += 32)
+            if (base + i < p.hit_cap) {
+                p.hit_keys[base + i] = em.st->keys[ob][i];
+                p.hit_scores[base + i] = em.st->scores[ob][i];
+            }
+        em.pend_n = 0;
+    }
+    const int n = min(em.st->n, kKmerStage);
+    __syncwarp();
+    if (n > 0) {
+        if (lane == 0) {
+            em.pend_base = atomicAdd(&p.counters[SMG_CTR_HITS_APPENDED], (unsigned long long)n);
+            em.st->n = 0;
+        }
+        em.pend_n = n;
+        em.cur ^= 1;
+    }
+    __syncwarp();
+}
 
 // direct scoring of one window that the index cannot serve (IUPAC code, 'Z', end padding): every PWM of the class
 __device__ __noinline__ void kmer_slow_window(const KmerParams& kp, const smg_row_t& row, const int r, const int W, const long long s,
-                                              unsigned long long* s_keys, float* s_scores, int* s_n, int* s_hist, unsigned* tallies)
+                                              KmerEmit& em, int* s_hist, unsigned* tallies)
 {
     const ScanParams& p = kp.sp;
     const int key_shift = p.pos_bits + p.motif_bits;
@@ -137,47 +199,43 @@ __device__ __noinline__ void kmer_slow_window(const KmerParams& kp, const smg_ro
             else if (p.counts) atomicAdd(p.counts + ((size_t)r * p.n_motifs + m) * 2 + st, 1);
             if (p.hit_keys) {
                 const long long pos = st ? (smax - s) : (row.g_off + s);
-                const unsigned long long key = ((unsigned long long)(unsigned)p.out_rows[r * 2 + st] << key_shift) |
-                                               ((unsigned long long)pos << p.motif_bits) | (unsigned long long)(unsigned)m;
-                const int slot = atomicAdd(s_n, 1);
-                if (slot < kKmerStage) {
-                    s_keys[slot] = key;
-                    s_scores[slot] = v;
-                } else {  // stage full (many generic windows at once): straight to the global list
-                    const unsigned long long gi = atomicAdd(&p.counters[SMG_CTR_HITS_APPENDED], 1ull);
-                    if (gi < p.hit_cap) {
-                        p.hit_keys[gi] = key;
-                        p.hit_scores[gi] = v;
-                    }
-                }
+                kmer_push(p, em, ((unsigned long long)(unsigned)p.out_rows[r * 2 + st] << key_shift) |
+                                     ((unsigned long long)pos << p.motif_bits) | (unsigned long long)(unsigned)m, v);
             }
         }
     }
 }
 
 // dynamic shared memory: [2 * n_motifs] int histogram (hist_in_smem) -- counts of this chunk's row
-__global__ void __launch_bounds__(kKmerThreads) scan_kmer_kernel(const KmerParams kp, const int hist_in_smem)
+__global__ void __launch_bounds__(kKmerThreads, 3) scan_kmer_kernel(const KmerParams kp, const int hist_in_smem)
 {
     const ScanParams& p = kp.sp;
     extern __shared__ int s_hist_dyn[];
-    __shared__ KmerStage st;
-    __shared__ int2 s_wq[kKmerThreads / 32][32 * kKmerMaxW];  // per-warp work queue: at most one item per (lane, class)
-    __shared__ int s_n;
-    __shared__ unsigned long long s_base;
+    __shared__ KmerWarpStage s_stage[kKmerThreads / 32];
+    __shared__ int2 s_wq[kKmerThreads / 32][kKmerQueue];  // per-warp work queue of non-empty lists
     __shared__ unsigned s_tally[3];
+    __shared__ uint32_t s_bm[kKmerSmemBitmapWords];  // bitmaps of the classes narrower than kKmerBitmapMinW
     int* s_hist = hist_in_smem && p.counts ? s_hist_dyn : nullptr;
     const smg_chunk_t ch = p.chunks[blockIdx.x];
     const smg_row_t row = p.rows[ch.row];
     const int c0 = ch.start, c1 = min(c0 + p.chunk_len, row.n_own);
     if (c1 <= c0) return;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    int2* wq = s_wq[tid >> 5];
+    int2* wq = s_wq[warp];
+    KmerEmit em;
+    em.st = &s_stage[warp]; em.cur = 0; em.pend_n = 0; em.pend_base = 0;
     const int key_shift = p.pos_bits + p.motif_bits;
     if (s_hist)
         for (int i = tid; i < 2 * p.n_motifs; i += kKmerThreads) s_hist[i] = 0;
-    if (tid == 0) s_n = 0;
+    if (lane == 0) s_stage[warp].n = 0;
     if (tid < 3) s_tally[tid] = 0;
+#pragma unroll
+    for (int W = 1; W < kKmerBitmapMinW; ++W) {
+        if (W > kp.max_w || kp.cls_off[W + 1] == kp.cls_off[W]) continue;
+        const int nw = kmer_bm_words(W);
+        for (int i = tid; i < nw; i += kKmerThreads) s_bm[kmer_sbm_off(W) + i] = (uint32_t)kp.head[kp.bm_off[W] + i];
+    }
     __syncthreads();
     const uint32_t* __restrict__ wp = p.packed + row.word_off;
     const uint16_t* __restrict__ ap = p.amask + row.word_off;
@@ -185,29 +243,22 @@ __global__ void __launch_bounds__(kKmerThreads) scan_kmer_kernel(const KmerParam
     const unsigned long long orow1 = (unsigned long long)(unsigned)p.out_rows[ch.row * 2 + 1] << key_shift;
     unsigned tallies[3] = {0, 0, 0};  // definite, near, accepted
     unsigned present = 0;
-    for (int W = 1; W <= kp.max_w; ++W)
-        if (kp.cls_off[W + 1] > kp.cls_off[W]) present |= 1u << W;
+    uint32_t hd32[kKmerMaxW + 1], bm32[kKmerMaxW + 1];  // 32-bit offsets of each class's heads / bitmap (the buffer has < 2^31 slots)
+#pragma unroll
+    for (int W = 1; W <= kKmerMaxW; ++W) {
+        hd32[W] = (uint32_t)kp.head_off[W];
+        bm32[W] = (uint32_t)kp.bm_off[W];
+        if (W <= kp.max_w && kp.cls_off[W + 1] > kp.cls_off[W]) present |= 1u << W;
+    }
+    const long long lim64 = (long long)row.g_len - (long long)row.g_off;
+    const int lim = lim64 > 0x7fffffffll ? 0x7fffffff : (int)lim64;  // windows must end inside the sequence
+    const int32_t* __restrict__ hd = kp.head;
+    const bool combined = kp.max_w > kKmerBitmapMinW;
+    const uint32_t cb32 = (uint32_t)kp.cb_off;
+    const uint32_t cb_mask = (uint32_t)((1ull << (2 * kp.max_w)) - 1ull);
 
-    auto flush = [&]() {  // all threads
-        __syncthreads();
-        const int n = min(s_n, kKmerStage);
-        if (n > 0 && p.hit_keys) {
-            if (tid == 0) s_base = atomicAdd(&p.counters[SMG_CTR_HITS_APPENDED], (unsigned long long)n);
-            __syncthreads();
-            const unsigned long long base = s_base;
-            for (int i = tid; i < n; i += kKmerThreads)
-                if (base + i < p.hit_cap) {
-                    p.hit_keys[base + i] = st.keys[i];
-                    p.hit_scores[base + i] = st.scores[i];
-                }
-        }
-        __syncthreads();
-        if (tid == 0) s_n = 0;
-        __syncthreads();
-    };
-
-    for (int pb = c0; pb < c1; pb += kKmerThreads) {
-        const int s = pb + tid;
+    for (int pb = c0 + warp * 32; pb < c1; pb += kKmerThreads) {  // this warp's 32 window starts of the CTA's stride
+        const int s = pb + lane;
         const bool active = s < c1;
         uint32_t win = 0, am = 0xffffu;
         if (active) {
@@ -217,49 +268,44 @@ __global__ void __launch_bounds__(kKmerThreads) scan_kmer_kernel(const KmerParam
             win = __funnelshift_r(p0, p1, 2 * sh);
             am = ((a0 | (a1 << 16)) >> sh) & 0xffffu;
         }
+        // which classes does this window start take through the index?  bit W set = class present, window inside the
+        // sequence (models.py:110 trim: W <= lim - s) and free of ambiguity codes (W <= index of the first flagged base)
+        unsigned ok = 0, slow = 0;
+        if (active) {
+            const int room = lim - s;                              // widest window that still fits
+            const unsigned m_trim = room >= kKmerMaxW ? 0xffffffffu : (room < 1 ? 0u : ((2u << room) - 1u));
+            const int clean = am ? (__ffs((int)am) - 1) : 16;      // bases before the first IUPAC code / 'Z' / padding
+            const unsigned m_clean = clean >= kKmerMaxW ? 0xffffffffu : ((2u << clean) - 1u);
+            ok = present & m_trim & m_clean;
+            slow = present & m_trim & ~m_clean;
+        }
         // ---- class lookups: one bitmap probe (wide classes: 95 % of the k-mers have no entry, and the 1-bit tables stay
-        // cache resident while the head tables do not) and one head load per class; the class loop is fully unrolled,
-        // `present` (bit W: the class has PWMs) is CTA-uniform.  Non-empty lists become work items of the warp's queue.
-        unsigned slow = 0;  // bit W: class W needs the generic path here
-        unsigned probe = 0; // bit W: class W has a list here
+        // cache resident while the head tables do not) and one head load per class; the class loop is fully unrolled
+        // narrow classes: bitmap in shared memory; wide classes: ONE probe of the combined bitmap (keyed by the widest
+        // class's k-mer: set iff any wide class has a list for its prefix) decides whether their own bitmaps are read
+        if (combined && (ok >> kKmerBitmapMinW)) {
+            const uint32_t y = win & cb_mask;
+            if (!(((uint32_t)hd[cb32 + (y >> 5)] >> (y & 31)) & 1u)) ok &= (1u << kKmerBitmapMinW) - 1u;
+        }
         uint32_t bmw[kKmerMaxW + 1];
 #pragma unroll
         for (int W = 1; W <= kKmerMaxW; ++W) {
-            bmw[W] = 0;
-            if (!((present >> W) & 1u) || !active) continue;
-            if ((long long)s > row.g_len - row.g_off - (long long)W) continue;  // models.py:110 trim
-            if (am & ((1u << W) - 1u)) { slow |= 1u << W; continue; }
-            if (W >= kKmerBitmapMinW) {
+            bmw[W] = (ok >> W) & 1u;
+            if (bmw[W]) {
                 const uint32_t x = win & (uint32_t)((1ull << (2 * W)) - 1ull);
-                bmw[W] = reinterpret_cast<const uint32_t*>(kp.head + kp.bm_off[W])[x >> 5] >> (x & 31);
-            } else {
-                bmw[W] = 1u;
+                if (W >= kKmerBitmapMinW) bmw[W] = (uint32_t)hd[bm32[W] + (x >> 5)] >> (x & 31);
+                else bmw[W] = s_bm[kmer_sbm_off(W) + (x >> 5)] >> (x & 31);
             }
         }
         int heads[kKmerMaxW + 1];
 #pragma unroll
         for (int W = 1; W <= kKmerMaxW; ++W) {
             heads[W] = -1;
-            if (bmw[W] & 1u) heads[W] = kp.head[kp.head_off[W] + (win & (uint32_t)((1ull << (2 * W)) - 1ull))];
+            if (bmw[W] & 1u) heads[W] = hd[hd32[W] + (win & (uint32_t)((1ull << (2 * W)) - 1ull))];
         }
-        // queue the non-empty lists: item = {entry index, (lane << 4) | W}; ballot + prefix popcount, no atomics
-        int qn = 0;
-#pragma unroll
-        for (int W = 1; W <= kKmerMaxW; ++W) {
-            if (!((present >> W) & 1u)) continue;
-            const bool has = heads[W] >= 0;
-            const unsigned bm = __ballot_sync(SMG_FULL_MASK, has);
-            if (has) wq[qn + __popc(bm & lt_mask)] = make_int2(heads[W], (lane << 4) | W);
-            qn += __popc(bm);
-        }
-        __syncwarp();
-        // ---- list walks with every lane busy: lane i takes item i, i + 32, ...
-        for (int qi = lane; qi < qn; qi += 32) {
-            const int2 item = wq[qi];
-            const int W = item.y & 15;
-            const int sp = pb + (tid & ~31) + (item.y >> 4);  // window start of the item
-            const long long smax = row.g_len - row.g_off - (long long)W;
-            int e = item.x;
+        // one list walk: every entry becomes a hit (or a tally, for k-mers the fp64 adjudicator rejected)
+        auto walk = [&](int e, const int W, const int sp) {
+            const int smax = lim - W;
             do {
                 const smg_kmer_entry_t ent = kp.entries[e];
                 e = ent.next;
@@ -271,40 +317,50 @@ __global__ void __launch_bounds__(kKmerThreads) scan_kmer_kernel(const KmerParam
                 if (s_hist) atomicAdd(&s_hist[col], 1);
                 else if (p.counts) atomicAdd(p.counts + ((size_t)ch.row * p.n_motifs + m) * 2 + sd, 1);
                 if (p.hit_keys) {
-                    const long long pos = sd ? (smax - sp) : (row.g_off + sp);
-                    const unsigned long long key = (sd ? orow1 : orow0) | ((unsigned long long)pos << p.motif_bits) |
-                                                   (unsigned long long)(unsigned)m;
-                    const int slot = atomicAdd(&s_n, 1);  // same address for the whole warp: the compiler aggregates it
-                    if (slot < kKmerStage) {
-                        st.keys[slot] = key;
-                        st.scores[slot] = ent.score;
-                    } else {  // stage full: straight to the global list (rare: the stage is flushed when half full)
-                        const unsigned long long gi = atomicAdd(&p.counters[SMG_CTR_HITS_APPENDED], 1ull);
-                        if (gi < p.hit_cap) {
-                            p.hit_keys[gi] = key;
-                            p.hit_scores[gi] = ent.score;
-                        }
-                    }
+                    const long long pos = sd ? (long long)(smax - sp) : (row.g_off + (long long)sp);
+                    kmer_push(p, em, (sd ? orow1 : orow0) | ((unsigned long long)pos << p.motif_bits) | (unsigned long long)(unsigned)m,
+                              ent.score);
                 }
             } while (e >= 0);
+        };
+        // queue the non-empty lists: item = {entry index, (lane << 4) | W}; ballot + prefix popcount, no atomics.  A list
+        // that does not fit in the queue (more than kKmerQueue non-empty lists in 32 window starts) is walked in place.
+        int qn = 0;
+#pragma unroll
+        for (int W = 1; W <= kKmerMaxW; ++W) {
+            if (!((present >> W) & 1u)) continue;
+            const bool has = heads[W] >= 0;
+            const unsigned bm = __ballot_sync(SMG_FULL_MASK, has);
+            if (has) {
+                const int qi = qn + __popc(bm & lt_mask);
+                if (qi < kKmerQueue) wq[qi] = make_int2(heads[W], (lane << 4) | W);
+                else walk(heads[W], W, s);
+            }
+            qn += __popc(bm);
+        }
+        qn = min(qn, kKmerQueue);
+        __syncwarp();
+        // ---- list walks with every lane busy: lane i takes item i, i + 32, ...
+        for (int qi = lane; qi < qn; qi += 32) {
+            const int2 item = wq[qi];
+            walk(item.x, item.y & 15, pb + (item.y >> 4));
         }
         __syncwarp();
-        // ---- generic path for windows the index cannot serve
-        if (__syncthreads_or(slow != 0u)) {
-            flush();  // the slow path appends through s_n one hit at a time: start from an empty stage
+        // ---- generic path for windows the index cannot serve (rare)
+        if (__any_sync(SMG_FULL_MASK, slow != 0u)) {
             if (slow) {
                 for (int W = 1; W <= kp.max_w; ++W)
-                    if ((slow >> W) & 1u) {
-                        // keep the stage from overflowing: at most 2 * class size hits per window
-                        kmer_slow_window(kp, row, ch.row, W, s, st.keys, st.scores, &s_n, s_hist, tallies);
-                    }
+                    if ((slow >> W) & 1u) kmer_slow_window(kp, row, ch.row, W, s, em, s_hist, tallies);
             }
-            flush();
-        } else if (s_n > kKmerStage / 2) {
-            flush();
+            __syncwarp();
         }
+        if (p.hit_keys && em.st->n > kKmerStage / 2) kmer_switch(p, em, lane);
     }
-    flush();
+    if (p.hit_keys) {  // drain: the active buffer becomes pending, then the last pending buffer is copied out
+        kmer_switch(p, em, lane);
+        kmer_switch(p, em, lane);
+    }
+    __syncthreads();
     if (s_hist && p.counts) {
         for (int i = tid; i < 2 * p.n_motifs; i += kKmerThreads) {
             const int v = s_hist[i];
@@ -350,6 +406,7 @@ int smg_kmer_fill_params(smg::KmerParams& kp, const std::vector<int>& widths, co
         kp.bm_off[W] = hoff;
         if (W >= 1 && W <= max_w && kp.cls_off[W + 1] > kp.cls_off[W]) hoff += std::max<int64_t>(1, (1ll << (2 * W)) >> 5);
     }
+    kp.cb_off = hoff;  // combined bitmap of the wide classes, keyed by the max_w-mer
     return 0;
 }
 
@@ -365,6 +422,7 @@ int64_t smg_kmer_head_len(const std::vector<int>& widths, int max_w, int64_t* n_
         }
     }
     if (n_heads) *n_heads = h;
+    if (h && max_w > smg::kKmerBitmapMinW) b += (1ll << (2 * std::min(max_w, smg::kKmerMaxW))) >> 5;  // combined bitmap
     return h ? h + b : 0;
 }
 
@@ -389,7 +447,7 @@ cudaError_t smg_kmer_launch_scan(const smg::KmerParams& kp, int n_chunks, cudaSt
 {
     const size_t hist_bytes = (size_t)kp.sp.n_motifs * 2 * sizeof(int);
     const int in_smem = hist_bytes <= 96 * 1024;
-    if (in_smem && hist_bytes > 8 * 1024) {
+    if (in_smem) {  // static + dynamic shared memory may exceed the 48 KB default
         cudaError_t e = cudaFuncSetAttribute(smg::scan_kmer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes);
         if (e != cudaSuccess) return e;
     }

@@ -9,11 +9,22 @@
 namespace smg {
 
 constexpr int kKmerMaxW = 12;
-constexpr int kKmerStage = 1024;         // hits staged per CTA before a flush
+constexpr int kKmerStage = 128;          // hits per buffer of a warp's double-buffered stage
+constexpr int kKmerQueue = 160;          // work items (non-empty lists) a warp queues per 32 window starts
 constexpr int kKmerBitmapMinW = 9;       // classes at least this wide are looked up through a 1-bit-per-k-mer bitmap first
 constexpr int kKmerThreads = 256;
 constexpr uint32_t kEntNear = 1u << 30;  // decided by the fp64 adjudicator
 constexpr uint32_t kEntRej = 1u << 29;   // inside the band, rejected in fp64 (kept so that the scan can count it)
+
+// bitmap words of class W, and where the narrow classes' bitmaps sit in the scan kernel's shared memory
+__host__ __device__ constexpr int kmer_bm_words(const int W) { return (1 << (2 * W)) >= 32 ? (1 << (2 * W)) / 32 : 1; }
+__host__ __device__ constexpr int kmer_sbm_off(const int W)
+{
+    int o = 0;
+    for (int w = 1; w < W; ++w) o += kmer_bm_words(w);
+    return o;
+}
+constexpr int kKmerSmemBitmapWords = kmer_sbm_off(kKmerBitmapMinW);
 
 struct KmerParams {
     ScanParams sp;
@@ -21,6 +32,7 @@ struct KmerParams {
     int32_t cls_off[kKmerMaxW + 2];   // class W = motifs cls_motifs[cls_off[W] .. cls_off[W + 1])
     int64_t head_off[kKmerMaxW + 2];  // first head slot of class W
     int64_t bm_off[kKmerMaxW + 2];    // first bitmap word of class W (in the same int32 buffer, after all heads)
+    int64_t cb_off;                   // combined bitmap of the classes >= kKmerBitmapMinW (max_w > kKmerBitmapMinW only)
     int32_t max_w;                    // classes 1 .. max_w
     int32_t* head;
     smg_kmer_entry_t* entries;
