@@ -66,3 +66,24 @@ def scan(code_rows, weights, frac_threshold, strands=3, out_rows=None, n_out_row
         o = np.argsort(keys[:n], kind="stable")
         res["keys"], res["scores"] = keys[:n][o], scores[:n][o]
     return res
+
+
+def variant_windows(code_row, weights, snv_pos, snv_alt_codes):
+    """Config c5: max reference / alternate window score per (SNV, PWM) over the windows covering the SNV, both strands
+    (fp32, kernel summation order).  code_row: uint8 integer codes of ONE sequence; snv_alt_codes: integer codes 0..16."""
+    lib = load()
+    w32 = [np.ascontiguousarray(np.asarray(w), dtype=np.float32) for w in weights]
+    widths = np.array([w.shape[0] for w in w32], dtype=np.int32)
+    tab_off = np.concatenate([[0], np.cumsum(widths)[:-1]]).astype(np.int64)
+    tab = np.ascontiguousarray(np.concatenate([w.reshape(-1) for w in w32]))
+    codes = np.ascontiguousarray(code_row, dtype=np.uint8)
+    pos = np.ascontiguousarray(snv_pos, dtype=np.int64)
+    alt = np.ascontiguousarray(snv_alt_codes, dtype=np.uint8)
+    n, M = len(pos), len(w32)
+    ref_max = np.empty((n, M), dtype=np.float32)
+    alt_max = np.empty((n, M), dtype=np.float32)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    lib.orc_variant_windows.restype = None
+    lib.orc_variant_windows(P(codes), ctypes.c_int64(len(codes)), P(tab), P(widths), P(tab_off), M, P(pos), P(alt),
+                            ctypes.c_int64(n), P(ref_max), P(alt_max))
+    return ref_max, alt_max

@@ -42,6 +42,8 @@ int orc_scan(const uint8_t* codes, const int64_t* row_off, const int64_t* row_le
             const int64_t L = row_len[r];
             const int W = widths[m];
             const float* T = tab + tab_off[m] * 4;
+            int finite_tab = 1;
+            for (int i = 0; i < 4 * W; ++i) finite_tab &= isfinite(T[i]) ? 1 : 0;
             for (int st = 0; st < 2; ++st) {
                 if (!((strands >> st) & 1)) continue;
                 int64_t cnt = 0;
@@ -52,10 +54,20 @@ int orc_scan(const uint8_t* codes, const int64_t* row_off, const int64_t* row_le
                         const float* tr = T + (st ? (W - 1 - k) : k) * 4;
                         const float t0 = st ? tr[3] : tr[0], t1 = st ? tr[2] : tr[1], t2 = st ? tr[1] : tr[2],
                                     t3 = st ? tr[0] : tr[3];
-                        const float* e = EMB[c[p + k]];
-                        const float term = ((e[0] * t0 + e[1] * t1) + e[2] * t2) + e[3] * t3;
-                        const double term64 = (((double)e[0] * (double)t0 + (double)e[1] * (double)t1) +
-                                               (double)e[2] * (double)t2) + (double)e[3] * (double)t3;
+                        const int code = c[p + k];
+                        float term;
+                        double term64;
+                        if (code >= 1 && code <= 5 && finite_tab) {
+                            /* plain base: the mix reduces to the selected weight exactly (1*t + 0 + 0 + 0, finite t) */
+                            const int b = code == 5 ? 3 : code - 1;
+                            term = b == 0 ? t0 : b == 1 ? t1 : b == 2 ? t2 : t3;
+                            term64 = (double)term;
+                        } else {
+                            const float* e = EMB[code];
+                            term = ((e[0] * t0 + e[1] * t1) + e[2] * t2) + e[3] * t3;
+                            term64 = (((double)e[0] * (double)t0 + (double)e[1] * (double)t1) +
+                                      (double)e[2] * (double)t2) + (double)e[3] * (double)t3;
+                        }
                         s32 = k ? s32 + term : term;
                         s64 = k ? s64 + term64 : term64;
                     }
@@ -82,4 +94,44 @@ int orc_scan(const uint8_t* codes, const int64_t* row_off, const int64_t* row_le
     }
     totals[0] = n_hits; totals[1] = n_near; totals[2] = ksum; totals[3] = kxor; totals[4] = n_flip;
     return overflow;
+}
+
+/* BASELINE config c5 (batched restatement of smeagol/variant.py:7-47 + scan.py:8-37): for every SNV (pos, alt code) on
+ * ONE row of integer codes and every PWM, the maximum fp32 window score over all windows that cover pos and lie inside
+ * the row, both strands, for the reference bases and with the base at pos replaced by alt.  Same fixed summation order
+ * as orc_scan ("kernel" order).  ref_max / alt_max: [n_snv][n_motifs]; -inf where no window fits. */
+void orc_variant_windows(const uint8_t* codes, int64_t L, const float* tab, const int32_t* widths, const int64_t* tab_off,
+                         int n_motifs, const int64_t* snv_pos, const uint8_t* snv_alt, int64_t n_snv, float* ref_max,
+                         float* alt_max)
+{
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t v = 0; v < n_snv; ++v) {
+        const int64_t pos = snv_pos[v];
+        for (int m = 0; m < n_motifs; ++m) {
+            const int W = widths[m];
+            const float* T = tab + tab_off[m] * 4;
+            float rmax = -INFINITY, amax = -INFINITY;
+            const int64_t s_lo = pos - W + 1 > 0 ? pos - W + 1 : 0;
+            const int64_t s_hi = pos < L - W ? pos : L - W;
+            for (int64_t s = s_lo; s <= s_hi; ++s)
+                for (int st = 0; st < 2; ++st) {
+                    float ra = 0.f, aa = 0.f;
+                    for (int k = 0; k < W; ++k) {
+                        const float* tr = T + (st ? (W - 1 - k) : k) * 4;
+                        const float t0 = st ? tr[3] : tr[0], t1 = st ? tr[2] : tr[1], t2 = st ? tr[1] : tr[2],
+                                    t3 = st ? tr[0] : tr[3];
+                        const float* e = EMB[codes[s + k]];
+                        const float* ea = (s + k == pos) ? EMB[snv_alt[v]] : e;
+                        const float tr_ref = ((e[0] * t0 + e[1] * t1) + e[2] * t2) + e[3] * t3;
+                        const float tr_alt = ((ea[0] * t0 + ea[1] * t1) + ea[2] * t2) + ea[3] * t3;
+                        ra = k ? ra + tr_ref : tr_ref;
+                        aa = k ? aa + tr_alt : tr_alt;
+                    }
+                    if (ra > rmax) rmax = ra;
+                    if (aa > amax) amax = aa;
+                }
+            ref_max[v * n_motifs + m] = rmax;
+            alt_max[v * n_motifs + m] = amax;
+        }
+    }
 }

@@ -167,3 +167,22 @@ def test_c_oracle_equals_numpy_oracle():
         np.testing.assert_array_equal((k & np.uint64((1 << mb) - 1)).astype(np.int64), exp["motif"])
         np.testing.assert_array_equal(res["scores"].view(np.uint32), exp["score"].view(np.uint32))
         assert res["n_hits"] == len(exp["row"]) and res["counts"].sum() == len(exp["row"])
+
+
+def test_c_variant_windows_equals_numpy_oracle():
+    """oracle/scan_oracle.c::orc_variant_windows (the checker of the config-c5 GPU test) against the numpy loop
+    restatement of variant.py:7-47 / scan.py:8-37 (fp64), incl. IUPAC codes near the SNVs and SNVs at the row ends."""
+    from oracle import c_oracle
+
+    rng = np.random.default_rng(71)
+    ws = []
+    for W in (3, 5, 8, 12, 17):
+        ws.append(np.log2((rng.dirichlet([0.5] * 4, size=W) + 0.01) / 1.04 / 0.25))
+    seq = "".join(rng.choice(list("ACGT"), size=120)) + "NRYACGTW" + "".join(rng.choice(list("ACGT"), size=90))
+    pos = np.concatenate([[0, 1, 2, len(seq) - 1, len(seq) - 2], rng.integers(0, len(seq), size=40)])
+    alts = [("ACGTN"[rng.integers(0, 5)]) for _ in pos]
+    e_ref, e_alt = so.variant_window_scan(seq, pos, alts, ws)
+    codes = so.integer_encode(seq).astype(np.uint8)
+    r, a = c_oracle.variant_windows(codes, ws, pos, [so.CODE_OF[x] for x in alts])
+    np.testing.assert_allclose(r, e_ref, rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(a, e_alt, rtol=1e-5, atol=2e-5)
