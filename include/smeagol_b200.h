@@ -126,6 +126,19 @@ int smg_pack(const uint8_t* d_src, int input_kind, const smg_row_t* d_rows, cons
 int smg_bin_hits(const uint64_t* d_keys, const float* d_scores, uint64_t n_hits, int pos_bits, int motif_bits,
                  const double* d_max_scores, const double* d_edges, int32_t n_bins, int32_t n_motifs, int32_t* d_hist, void* stream);
 
+/* matrices.pairwise_ncorrs (matrices.py:396-433) on the device ("next" row 8(f)-4): all pairwise normalised Pearson
+ * correlations (max over the alignments of align_pms and over the four orientation combinations, exactly as ncorr and
+ * the reference's reverse_complement compute them) of n position matrices.  d_mats: the matrices concatenated row-major
+ * (sum of widths x 4 doubles), d_offs[m] = first row of matrix m; d_out: n x n doubles (symmetric, diagonal 1). */
+int smg_pairwise_ncorrs(const double* d_mats, const int32_t* d_widths, const int64_t* d_offs, int32_t n, double* d_out, void* stream);
+
+/* scan.count_in_sliding_windows (scan.py:381-423) on the device ("next" row 8(f)-4): for every hit whose PWM is selected
+ * (d_motif_sel[motif] != 0) one count in each tiling window [k*shift, k*shift + width) of its record that contains the hit's
+ * start.  d_row_rec[out_row] = record index of an output row (-1: ignore); record r owns the windows d_win_off[r] ..
+ * d_win_off[r+1] of d_counts (zeroed by the caller).  The hit list may be unsorted. */
+int smg_window_counts(const uint64_t* d_keys, uint64_t n_hits, int pos_bits, int motif_bits, const uint8_t* d_motif_sel,
+                      const int32_t* d_row_rec, const int64_t* d_win_off, int64_t width, int64_t shift, int32_t* d_counts, void* stream);
+
 /* utils.shuffle_records (utils.py:36-83) on the device ("next" row 8(f)-1): n_copies k-mer preserving shuffles of one
  * sequence, all in one launch.  d_tok: the sequence as integer codes 0..16 (len bytes).  k = 2 (dinucleotide, the
  * published algorithm of deeplift.dinuc_shuffle): d_succ = the successors tok[i+1] bucketed by tok[i] in original order

@@ -4,7 +4,7 @@ Drop-in for the reference's ``smeagol.encode`` / ``smeagol.models.PWMModel`` / `
 scan calls of ``smeagol.enrich`` and a batched ``smeagol.variant``): ``import smeagol_b200 as smeagol``.
 """
 from . import encode, io, models, scan, utils  # noqa: F401
-from . import enrich, variant  # noqa: F401
+from . import enrich, matrices, variant  # noqa: F401
 from .seqrecord import Seq, SeqRecord  # noqa: F401
 
 __version__ = "0.1.0"

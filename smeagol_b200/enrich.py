@@ -84,3 +84,81 @@ def enrich_in_genome(records, model, rcomp, threshold, simN=1000, simK=2, sense=
     if verbose:
         results["shuf_seqs"] = shuf
     return results
+
+
+def examine_thresholds(records, model, simN=300, simK=2, rcomp="only", min_threshold=0.5, threshold_shift=0.1, sense="+",
+                       verbose=False, combine_seqs=True):
+    """Number of binding sites at different cut-offs of the match score, for the real sequence(s) and for shuffled
+    ones (enrich.py:206-284; same arguments and result keys 'real_binned', 'shuf_binned').  Both scans histogram the
+    device hit list in place (smg_bin_hits), the shuffles are generated on the device."""
+    thresholds = np.arange(min_threshold, 1.0, threshold_shift)
+    real_binned = scan_sequences(records, model, thresholds, sense, rcomp, outputs=["binned_counts"],
+                                 combine_seqs=combine_seqs)["binned_counts"]
+    shuf = shuffle_records(records, simN, simK)
+    shuf_binned = scan_sequences(shuf, model, thresholds, sense, rcomp, outputs=["binned_counts"], combine_seqs=combine_seqs,
+                                 group_by="name", sep_ids=True)["binned_counts"]
+    results = {"real_binned": real_binned, "shuf_binned": shuf_binned}
+    if verbose:
+        results["shuf_seqs"] = shuf
+    return results
+
+
+def _fisher_window_rows(windows, counts, tot_count, width, genome, alternative):
+    """The per-window statistics of enrich_in_window (enrich.py:320-338) for a frame of windows."""
+    result = windows.copy()
+    effective_genome_len = sum(len(x) for x in genome) - width + 1
+    result["len"] = result.end - result.start - width + 1
+    result["count"] = counts
+    result["tot_count"] = tot_count
+    result["expected"] = (result.tot_count * result.len) / effective_genome_len
+    tot_neg = effective_genome_len - tot_count
+    odds, ps = [], []
+    for c, ln in zip(result["count"], result["len"]):
+        o, p = stats.fisher_exact([[c, ln - c], [tot_count, tot_neg]], alternative=alternative)
+        odds.append(o)
+        ps.append(p)
+    result["odds"] = odds
+    result["p"] = ps
+    return result
+
+
+def _sites_of_matrix(sites, matrix_id):
+    """(total sites of the PWM, its width) from a sites DataFrame or a DeviceSites."""
+    from .scan import DeviceSites
+
+    if isinstance(sites, DeviceSites):
+        import torch
+
+        m = sites.model
+        sel = np.flatnonzero(np.asarray(m.Matrix_ids) == matrix_id)
+        k = sites.res.keys[:sites.res.n_hits]
+        motif = k & ((1 << sites.res.motif_bits) - 1)
+        tot = int(torch.isin(motif, torch.from_numpy(sel).to(k.device)).sum().item()) if sites.res.n_hits else 0
+        return tot, int(m.widths[sel[0]])
+    matrix_sites = sites[sites.Matrix_id == matrix_id].reset_index(drop=True)
+    return len(matrix_sites), int(matrix_sites.width[0])
+
+
+def enrich_in_window(window, sites, genome, matrix_id=None, alternative="two-sided"):
+    """Fisher's exact test for enrichment of a PWM's sites in one window relative to the whole genome (enrich.py:287-338;
+    `window`: a row / one-row frame with id, start, end)."""
+    from .scan import _count_in_window
+
+    tot, width = _sites_of_matrix(sites, matrix_id)
+    w = window.to_frame().T if isinstance(window, pd.Series) else window
+    counts = [_count_in_window(row, sites, matrix_id) for _, row in w.iterrows()]
+    res = _fisher_window_rows(w, counts, tot, width, genome, alternative)
+    return res.iloc[0] if isinstance(window, pd.Series) else res
+
+
+def enrich_in_sliding_windows(sites, genome, width, shift=None, matrix_id=None, alternative="two-sided"):
+    """Enrichment of a PWM's sites in sliding windows across a genome (enrich.py:341-374): tiling windows, window counts
+    (on the device when `sites` is a scan.DeviceSites), Fisher's exact test per window, overall BH-FDR (`padj`)."""
+    from .scan import count_in_sliding_windows
+
+    counted = count_in_sliding_windows(sites, genome, matrix_id, width, shift)
+    tot, mwidth = _sites_of_matrix(sites, matrix_id)
+    windows = _fisher_window_rows(counted[["id", "start", "end"]], counted["count"].to_numpy(), tot, mwidth, genome,
+                                  alternative).reset_index(drop=True)
+    windows["padj"] = _fdrcorrection(windows.p)
+    return windows

@@ -360,23 +360,71 @@ def scan_sequences(seqs, model, threshold, sense="+", rcomp="none", outputs=["si
                                  combine_seqs=combine_seqs, sep_ids=sep_ids, seq_batch=seq_batch)
 
 
-# ---------------------------------------------------------------------- analysis in windows (host, scan.py:381-423)
-def _tiling_windows(genome, width, shift=None):
-    shift = width if shift is None else shift
-    frames = []
-    for record in genome:
-        starts = np.arange(0, len(record), shift)
-        frames.append(pd.DataFrame({"id": np.tile(record.id, len(starts)), "start": starts,
-                                    "end": np.minimum(starts + width, len(record))}))
-    return pd.concat(frames) if len(frames) > 1 else frames[0]
+# ---------------------------------------------------------------------- analysis in windows (scan.py:381-423)
+class DeviceSites:
+    """The sites of one scan kept on the device (sorted hit keys + the row layout), for consumers that never need the
+    DataFrame: count_in_sliding_windows / enrich_in_sliding_windows histogram them in place (smg_window_counts)."""
+
+    def __init__(self, res, layout, groups, model):
+        self.res, self.layout, self.groups, self.model = res, layout, groups, model
+        self.row_ids = np.concatenate([g.ids for g in groups]).astype(object)  # id of every output row
+
+    def __len__(self):
+        return int(self.res.n_hits)
+
+
+def scan_sequences_device(seqs, model, threshold, sense="+", rcomp="none", group_by=None):
+    """scan_sequences(..., outputs=['sites']) that leaves the site list on the device (DeviceSites)."""
+    encoded = SeqGroups(seqs, rcomp=rcomp, sense=sense, group_by=group_by)
+    res, layout = _device_scan_groups(encoded, model, threshold, want_hits=True, want_counts=False, sort=False)
+    return DeviceSites(res, layout, encoded.seqs, model)
+
+
+def _count_in_window(window, sites, matrix_id=None):
+    """Count of sites of one PWM whose start lies in a window (scan.py:381-401)."""
+    sel = (sites.id == window.id) & (sites.start >= window.start) & (sites.start < window.end)
+    if matrix_id is not None:
+        sel &= sites.Matrix_id == matrix_id
+    return int(sel.sum())
+
+
+def _window_counts_device(dsites, windows, genome, matrix_id, width, shift):
+    import torch
+
+    from . import _lib
+
+    res, model = dsites.res, dsites.model
+    d = res.keys.device if res.keys is not None else dev._require_cuda()
+    rec_of = {r.id: i for i, r in enumerate(genome)}
+    n_win = np.array([len(np.arange(0, len(r), shift)) for r in genome], dtype=np.int64)
+    win_off = np.concatenate([[0], np.cumsum(n_win)]).astype(np.int64)
+    row_rec = np.array([rec_of.get(i, -1) for i in dsites.row_ids], dtype=np.int32)
+    sel = np.ones(model.channels, dtype=np.uint8) if matrix_id is None else (np.asarray(model.Matrix_ids) == matrix_id).astype(np.uint8)
+    counts = torch.zeros(max(int(win_off[-1]), 1), dtype=torch.int32, device=d)
+    if res.n_hits:
+        # named tensors: a temporary would be freed (and its block reused by the next upload) before the call is made
+        d_sel, d_rec, d_off = torch.from_numpy(sel).to(d), torch.from_numpy(row_rec).to(d), torch.from_numpy(win_off).to(d)
+        with torch.cuda.device(d):
+            _lib.check(_lib.load().smg_window_counts(dev._ptr(res.keys), res.n_hits, res.pos_bits, res.motif_bits, dev._ptr(d_sel),
+                                                     dev._ptr(d_rec), dev._ptr(d_off), int(width), int(shift), dev._ptr(counts),
+                                                     dev._stream()), "smg_window_counts")
+    return counts[:int(win_off[-1])].cpu().numpy().astype(np.int64)
 
 
 def count_in_sliding_windows(sites, genome, matrix_id, width, shift=None):
-    """Count binding sites of one PWM in sliding windows (scan.py:404-423), vectorised with searchsorted."""
-    windows = _tiling_windows(genome, width, shift).reset_index(drop=True)
+    """Count binding sites in sliding windows across a genome (scan.py:404-423; same arguments and frame: id, start, end,
+    count).  `sites` is the reference's sites DataFrame (counted on the host with two binary searches per record instead
+    of one boolean mask per window) or a DeviceSites from scan_sequences_device (histogram on the device)."""
+    from .utils import get_tiling_windows_over_genome
+
+    shift_ = width if shift is None else shift
+    windows = get_tiling_windows_over_genome(genome, width, shift).reset_index(drop=True)
+    if isinstance(sites, DeviceSites):
+        windows["count"] = _window_counts_device(sites, windows, genome, matrix_id, width, shift_)
+        return windows
     sel = sites if matrix_id is None else sites[sites.Matrix_id == matrix_id]
     counts = np.zeros(len(windows), dtype=np.int64)
-    for rid, idx in windows.groupby("id").groups.items():
+    for rid, idx in windows.groupby("id", sort=False).groups.items():
         st = np.sort(sel.start[sel.id == rid].to_numpy())
         w = windows.loc[idx]
         counts[np.asarray(idx)] = np.searchsorted(st, w.end.to_numpy(), "left") - np.searchsorted(st, w.start.to_numpy(), "left")

@@ -56,6 +56,25 @@ def read_bg_seqs(file, records, simN):
     return bg
 
 
+def _get_tiling_windows_over_record(record, width, shift):
+    """Tiling windows over one sequence (utils.py:135-155): id, start, end."""
+    import pandas as pd
+
+    starts = np.arange(0, len(record), shift)
+    return pd.DataFrame({"id": np.tile(record.id, len(starts)), "start": starts, "end": np.minimum(starts + width, len(record))})
+
+
+def get_tiling_windows_over_genome(genome, width, shift=None):
+    """Tiling windows over every sequence of a genome (utils.py:158-180); shift defaults to width."""
+    import pandas as pd
+
+    if shift is None:
+        shift = width
+    if len(genome) == 1:
+        return _get_tiling_windows_over_record(genome[0], width, shift)
+    return pd.concat([_get_tiling_windows_over_record(record, width, shift) for record in genome])
+
+
 def get_site_seq(site, seqs):
     """Sequence of a binding site, sliced from the FORWARD record (utils.py:183-195)."""
     if type(seqs) == str:

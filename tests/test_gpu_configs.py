@@ -272,3 +272,107 @@ def test_shuffle_fixture_of_the_reference():
     # k = 1: a permutation of the bases
     shuf1 = sb.utils.shuffle_records(genome, 2, 1)
     assert sorted(str(shuf1[0].seq)) == sorted(str(genome[0].seq)) and sorted(str(shuf1[3].seq)) == sorted(str(genome[1].seq))
+
+
+def _golden_f4():
+    import json
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden_f4.json")) as f:
+        return json.load(f)
+
+
+def test_pairwise_ncorrs_device_replays_the_reference():
+    """matrices.pairwise_ncorrs on the device (smg_pairwise_ncorrs, one thread per pair, fp64) against
+    outputs recorded from the unmodified reference (test PWMs; 15 random PWMs of widths 3..20 incl. a duplicate) and
+    against the CPU oracle on 120 random PWMs."""
+    import smeagol_b200 as sb
+    from golden_util import golden, pwms_from_json
+    from oracle import matrix_oracle as mo
+
+    G = _golden_f4()
+    tp = pwms_from_json(golden()["test_pwms"])[1]
+    np.testing.assert_allclose(sb.matrices.pairwise_ncorrs(tp), np.array(G["pairwise_test_pwms"]["result"]), rtol=0, atol=1e-12)
+    R = G["pairwise_random"]
+    got = sb.matrices.pairwise_ncorrs([np.array(w) for w in R["weights"]])
+    np.testing.assert_allclose(got, np.array(R["result"]), rtol=0, atol=1e-12)
+    assert got[0, 14] == pytest.approx(1.0, abs=1e-12) and np.all(np.diag(got) == 1.0) and np.array_equal(got, got.T)
+    rng = np.random.default_rng(91)
+    mats = [np.log2((rng.dirichlet([0.5] * 4, size=int(rng.integers(1, 25))) + 0.01) / 1.04 / 0.25) for _ in range(120)]
+    mats[7] = np.zeros((4, 4))  # zero variance: NaN correlations, Python max() semantics
+    with np.errstate(invalid="ignore", divide="ignore"):
+        exp = mo.pairwise_ncorrs(mats)
+    got = sb.matrices.pairwise_ncorrs(mats)
+    np.testing.assert_allclose(got, exp, rtol=0, atol=1e-12, equal_nan=True)
+    assert np.isnan(exp[7, 3])
+
+
+def test_window_counts_and_thresholds_on_device_replay_the_reference(monkeypatch):
+    """scan.count_in_sliding_windows / enrich.enrich_in_sliding_windows on sites that never leave the device
+    (scan.scan_sequences_device + smg_window_counts), and enrich.examine_thresholds (device binned counts), against
+    outputs recorded from the unmodified reference (tests/golden/make_golden_f4.py)."""
+    import smeagol_b200 as sb
+    from golden_util import assert_frame_matches
+
+    G = _golden_f4()
+    Wd = G["windows"]
+    genome = [sb.SeqRecord(sb.Seq(s), id=i, name=i) for s, i in zip(Wd["seqs"], Wd["ids"])]
+    pw = pd.DataFrame({"Matrix_id": Wd["pwms"]["Matrix_id"], "weights": [np.array(w) for w in Wd["pwms"]["weights"]]})
+    model = sb.models.PWMModel(pw)
+    dsites = sb.scan.scan_sequences_device(genome, model, Wd["threshold"], sense="+", rcomp="both")
+    assert len(dsites) == Wd["n_sites"]
+    for case in Wd["cases"]:
+        cnt = sb.scan.count_in_sliding_windows(dsites, genome, Wd["matrix_id"], case["width"], case["shift"])
+        for c in ("id", "start", "end", "count"):
+            assert list(cnt[c]) == list(case["counts"][c]), c
+        enr = sb.enrich.enrich_in_sliding_windows(dsites, genome, case["width"], case["shift"], matrix_id=Wd["matrix_id"])
+        exp = case["enrich"]
+        assert list(enr.columns) == list(exp.keys())
+        for c in ("id", "start", "end", "len", "count", "tot_count"):
+            assert list(enr[c]) == list(exp[c]), c
+        for c in ("expected", "odds", "p", "padj"):
+            np.testing.assert_allclose(enr[c].astype(float), np.array(exp[c], dtype=float), rtol=1e-9, atol=1e-12, err_msg=c)
+    # every PWM at once (matrix_id=None) against the host route on the DataFrame of the same scan
+    sites = sb.scan.scan_sequences(genome, model, Wd["threshold"], sense="+", rcomp="both", outputs=["sites"])["sites"]
+    a = sb.scan.count_in_sliding_windows(dsites, genome, None, 150, 50)
+    b = sb.scan.count_in_sliding_windows(sites, genome, None, 150, 50)
+    assert list(a["count"]) == list(b["count"]) and a["count"].sum() > len(sites)
+    # examine_thresholds: the recorded run used reversed records as its "shuffles" (deterministic stand-in)
+    def fake_shuffle(records, simN, simK=2, **kw):
+        return [sb.SeqRecord(sb.Seq(str(r.seq)[::-1]), id="background_seq_%d" % i, name=r.id) for r in records for i in range(simN)]
+
+    monkeypatch.setattr(sb.enrich, "shuffle_records", fake_shuffle)
+    # A perfect match has frac_score = fp32 score / fp64 max_score = 1 +- 1 ulp: whether it is inside the last bin
+    # (0.9, 1.0] depends on the fp32 summation order, which the reference leaves to its conv backend.  Cells of that bin
+    # may therefore differ by at most the number of such sites (north_star: scores within 1e-5); everything else is exact.
+    def perfect_sites(recs, keys, **kw):
+        st = sb.scan.scan_sequences(recs, model, 0.5, sense="+", rcomp="both", outputs=["sites"], score=True, **kw)["sites"]
+        st = st[np.abs(st.frac_score - 1.0) < 1e-6]
+        return st.groupby(keys).size().to_dict() if len(st) else {}
+
+    def check_binned(got, exp, name, slack):
+        exp = pd.DataFrame(exp)
+        got = got.copy()
+        got["bin"] = got["bin"].astype(str)
+        assert list(got.columns) == list(exp.columns) and len(got) == len(exp), name
+        keys = [c for c in exp.columns if c not in ("num", "bin")]
+        for c in exp.columns:
+            if c != "num":
+                assert list(got[c]) == list(exp[c]), (name, c)
+        diff = np.flatnonzero(got["num"].to_numpy() != exp["num"].to_numpy())
+        for i in diff:
+            assert got["bin"].iloc[i] == "(0.9, 1.0]", (name, got.iloc[i].to_dict())
+            k = tuple(got[c].iloc[i] for c in slack[0])
+            assert abs(int(got["num"].iloc[i]) - int(exp["num"].iloc[i])) <= slack[1].get(k if len(k) > 1 else k[0], 0), (name, k)
+        return len(diff)
+
+    n_diff = 0
+    for combine in (True, False):
+        res = sb.enrich.examine_thresholds(genome, model, simN=2, simK=2, rcomp="both", min_threshold=0.5, threshold_shift=0.1,
+                                           combine_seqs=combine)
+        exp = G["examine_thresholds_combine_%s" % combine]
+        rkeys = ["Matrix_id", "sense"] + ([] if combine else ["id"])
+        skeys = ["Matrix_id", "sense", "id"] + ([] if combine else ["name"])
+        n_diff += check_binned(res["real_binned"], exp["real_binned"], "real_binned", (rkeys, perfect_sites(genome, rkeys)))
+        n_diff += check_binned(res["shuf_binned"], exp["shuf_binned_reversed_records"], "shuf_binned",
+                               (skeys, perfect_sites(fake_shuffle(genome, 2), skeys, group_by="name")))
+    assert n_diff <= 8  # a handful of perfect-match sites in 4 x 240 cells

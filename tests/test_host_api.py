@@ -289,3 +289,51 @@ def test_device_seq_behaves_like_a_seq():
     assert list(enc.seqs[0][:4]) == [1, 2, 3, 4]
     with pytest.raises(ValueError):
         sb.encode.SeqEncoding([rec, sb.SeqRecord(sb.Seq("ACG"), id="z", name="z")], rcomp="none", sense="+")
+
+
+def _golden_f4():
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden_f4.json")) as f:
+        return json.load(f)
+
+
+def test_window_and_similarity_host_functions_replay_the_reference():
+    """Host halves of the SURVEY 8(f) rank-4 rows against outputs recorded from the unmodified reference
+    (tests/golden/make_golden_f4.py): matrices.ncorr and its helpers, utils.get_tiling_windows_over_genome,
+    scan.count_in_sliding_windows on a sites DataFrame, enrich.enrich_in_sliding_windows (Fisher + FDR)."""
+    import pandas as pd
+
+    import smeagol_b200 as sb
+    from oracle import frames as of
+
+    G = _golden_f4()
+    k = G["ncorr_kat"]
+    X, Y = np.array(k["X"]), np.array(k["Y"])
+    assert sb.utils._equals(sb.matrices.ncorr(X, Y, min_overlap=3), 0.25069190635147276)  # tests/test_matrices.py:193-196
+    assert abs(sb.matrices.ncorr(Y, X, min_overlap=3) - k["result_swapped"]) < 1e-12
+    assert list(sb.matrices.align_pms(X, Y)) == [(0, 3, 0, 3), (0, 3, 1, 4), (0, 3, 2, 5)]
+    rc = sb.matrices.reverse_complement(Y)
+    assert np.array_equal(rc, Y[:, ::-1])  # the reference's function as written: columns swapped, rows kept
+    with pytest.raises(ValueError):
+        sb.matrices.matrix_correlation(X, Y)
+    Wd = G["windows"]
+    genome = [sb.SeqRecord(sb.Seq(s), id=i, name=i) for s, i in zip(Wd["seqs"], Wd["ids"])]
+    sites = of.scan_sequences(Wd["seqs"], Wd["ids"], Wd["ids"], Wd["pwms"]["Matrix_id"], [np.array(w) for w in Wd["pwms"]["weights"]],
+                              Wd["threshold"], sense="+", rcomp="both", outputs=["sites"], score=True)["sites"]
+    for case in Wd["cases"]:
+        w = sb.utils.get_tiling_windows_over_genome(genome, case["width"], case["shift"]).reset_index(drop=True)
+        for c in ("id", "start", "end"):
+            assert list(w[c]) == list(case["windows"][c])
+        cnt = sb.scan.count_in_sliding_windows(sites, genome, Wd["matrix_id"], case["width"], case["shift"])
+        assert list(cnt.columns) == ["id", "start", "end", "count"] and list(cnt["count"]) == list(case["counts"]["count"])
+        enr = sb.enrich.enrich_in_sliding_windows(sites, genome, case["width"], case["shift"], matrix_id=Wd["matrix_id"])
+        exp = case["enrich"]
+        assert list(enr.columns) == list(exp.keys())
+        for c in ("id", "start", "end", "len", "count", "tot_count"):
+            assert list(enr[c]) == list(exp[c]), c
+        for c in ("expected", "odds", "p", "padj"):
+            np.testing.assert_allclose(enr[c].astype(float), np.array(exp[c], dtype=float), rtol=1e-9, atol=1e-12, err_msg=c)
+        one = sb.enrich.enrich_in_window(w.iloc[1], sites, genome, matrix_id=Wd["matrix_id"])
+        assert one["count"] == exp["count"][1] and abs(float(one["p"]) - exp["p"][1]) < 1e-12

@@ -1,6 +1,8 @@
 """CPU tests: the oracle (oracle/scan_oracle.py, oracle/frames.py) replayed against every golden vector the
 reference's own tests hold for the scan path, and against outputs of the reference's modules recorded by
 tests/golden/make_golden.py.  This is what pins the oracle (parity status: PINNED)."""
+import os
+
 import numpy as np
 import pandas as pd
 import pytest
@@ -186,3 +188,41 @@ def test_c_variant_windows_equals_numpy_oracle():
     r, a = c_oracle.variant_windows(codes, ws, pos, [so.CODE_OF[x] for x in alts])
     np.testing.assert_allclose(r, e_ref, rtol=1e-5, atol=2e-5)
     np.testing.assert_allclose(a, e_alt, rtol=1e-5, atol=2e-5)
+
+
+def _golden_f4():
+    import json
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden_f4.json")) as f:
+        return json.load(f)
+
+
+def test_matrix_oracle_replays_reference_ncorr_and_windows():
+    """oracle/matrix_oracle.py against outputs recorded from the unmodified reference (tests/golden/make_golden_f4.py):
+    tests/test_matrices.py:176-213's known answers, pairwise_ncorrs on 15 random PWMs (widths 3..20, one duplicate),
+    tiling windows and count_in_sliding_windows on the sites of a recorded scan."""
+    from oracle import matrix_oracle as mo
+
+    G = _golden_f4()
+    k = G["ncorr_kat"]
+    assert abs(mo.ncorr(np.array(k["X"]), np.array(k["Y"])) - 0.25069190635147276) < 1e-9
+    assert abs(mo.ncorr(np.array(k["Y"]), np.array(k["X"])) - k["result_swapped"]) < 1e-12
+    tp = pwms_from_json(golden()["test_pwms"])[1]
+    np.testing.assert_allclose(mo.pairwise_ncorrs(tp), np.array(G["pairwise_test_pwms"]["result"]), rtol=0, atol=1e-12)
+    # (tests/test_matrices.py:199-213 expects 0.46869686 / 0.98630056 / 0.46716826 here; the unmodified module returns the
+    # recorded values -- its reverse_complement does not reverse the rows, see oracle/matrix_oracle.py)
+    R = G["pairwise_random"]
+    got = mo.pairwise_ncorrs([np.array(w) for w in R["weights"]])
+    np.testing.assert_allclose(got, np.array(R["result"]), rtol=0, atol=1e-12)
+    assert abs(got[0, 14] - 1.0) < 1e-12
+    Wd = G["windows"]
+    sites = of.scan_sequences(Wd["seqs"], Wd["ids"], Wd["ids"], Wd["pwms"]["Matrix_id"], [np.array(w) for w in Wd["pwms"]["weights"]],
+                              Wd["threshold"], sense="+", rcomp="both", outputs=["sites"], score=True)["sites"]
+    assert len(sites) == Wd["n_sites"]
+    lens = [len(s) for s in Wd["seqs"]]
+    for case in Wd["cases"]:
+        w = mo.tiling_windows(Wd["ids"], lens, case["width"], case["shift"]).reset_index(drop=True)
+        for c in ("id", "start", "end"):
+            assert list(w[c]) == list(case["windows"][c])
+        cnt = mo.count_in_sliding_windows(sites, Wd["ids"], lens, Wd["matrix_id"], case["width"], case["shift"])
+        assert list(cnt["count"]) == list(case["counts"]["count"]) and sum(cnt["count"]) > 0
