@@ -278,6 +278,7 @@ def run_c4(args, rank, world, local_rank, device, peaks, peaks_kind, warmup):
     plan.launch()
     res0 = plan.finish(sort=False)  # calibrates the hit buffer; the workload is deterministic
     n_hits = res0.n_hits
+    batch_own = batch.total_own
     keys_out = torch.empty(max(n_hits, 1), dtype=torch.int64, device=device)
     scores_out = torch.empty(max(n_hits, 1), dtype=torch.float32, device=device)
     sort_tmp = torch.empty(16, dtype=torch.uint8, device=device)
@@ -307,7 +308,7 @@ def run_c4(args, rank, world, local_rank, device, peaks, peaks_kind, warmup):
                 ev[2].record()
         if n_hits:
             _, _, sort_tmp = dev.sort_hits(plan.keys, plan.scores, n_hits, plan.key_bits, keys_out, scores_out, sort_tmp,
-                                           return_temp=True)
+                                           return_temp=True, motif_bits=plan.motif_bits, total_positions=2 * batch_own)
         if ev:
             ev[3].record()
         torch.sum(plan.counts, dim=0, keepdim=True, out=gcounts)
@@ -473,7 +474,8 @@ def run_c2(args, rank, world, local_rank, device, peaks, peaks_kind, warmup, ste
                 ev[1].record()
         if ev:
             ev[2].record()
-        dev.sort_hits(plan.keys, plan.scores, n_hits, plan.key_bits, keys_out, scores_out, sort_tmp)
+        dev.sort_hits(plan.keys, plan.scores, n_hits, plan.key_bits, keys_out, scores_out, sort_tmp, motif_bits=plan.motif_bits,
+                      total_positions=2 * total_bases)
         if world > 1:
             dist.all_gather_into_tensor(gathered, plan.counts)
         if ev:

@@ -19,7 +19,7 @@ NEAR_BYTES = 24
 EXPORTS = [
     "smg_version", "smg_last_error", "smg_launch_count", "smg_pwmset_create", "smg_pwmset_create_split", "smg_pwmset_create_split3",
     "smg_kmer_index_size", "smg_kmer_index_build", "smg_scan_kmer", "smg_pwmset_destroy", "smg_pwmset_info",
-    "smg_pack", "smg_scan", "smg_scan_tc", "smg_scan_tc5", "smg_adjudicate", "smg_sort_hits", "smg_predict_dense", "smg_variant_sites",
+    "smg_pack", "smg_scan", "smg_scan_tc", "smg_scan_tc5", "smg_adjudicate", "smg_sort_hits", "smg_sort_hits_bucketed", "smg_predict_dense", "smg_variant_sites",
     "smg_variant_windows", "smg_pairwise_ncorrs", "smg_window_counts", "smg_fasta_index", "smg_fasta_compact", "smg_kmer_shuffle", "smg_bin_hits",
 ]
 
@@ -68,6 +68,7 @@ def load():
     lib.smg_fasta_compact.argtypes = [vp, i64, vp, i64, vp, vp, vp, vp, ctypes.c_int, vp, ctypes.POINTER(u64), vp]
     lib.smg_adjudicate.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u64, ctypes.c_int, ctypes.c_int, vp, vp, u64, vp, vp, vp]
     lib.smg_sort_hits.argtypes = [vp, vp, vp, vp, u64, ctypes.c_int, vp, ctypes.POINTER(u64), vp]
+    lib.smg_sort_hits_bucketed.argtypes = [vp, vp, vp, vp, u64, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(u64), vp, vp]
     lib.smg_predict_dense.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp]
     lib.smg_variant_sites.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp]
     lib.smg_variant_windows.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp]

@@ -243,71 +243,77 @@ __global__ void __launch_bounds__(kTc5Threads, 1) scan_tc5_kernel(const __grid_c
             for (int t0 = c0; t0 < c1; t0 += kTc5Tile) {
                 for (int b = 0; b < n_blk; ++b) {
                     const float thr = hp.thr_pre_col[col0 + b * 128];
-                    const int cid = hp.col_id[col0 + b * 128];
                     for (int e = 0; e < 2; ++e, ++gcount) {
                         const int buf = gcount & 1;
                         tc5::mbar_wait(&ms.tfull[buf], (uint32_t)((gcount >> 1) & 1));
                         tc5::fence_after_sync();
-                        // two halves of 32 cells: 18 warps leave 96 registers per thread (5 warps share a 16 K sub-partition)
+                        // both halves of the 64 cells are requested back to back (one TMEM round trip instead of two), then the
+                        // accumulator is handed back to the MMA issuer before any arithmetic
+                        uint32_t r[2][32];
+                        tc5::tmem_ld_32x32b_x32(r[0], taddr0 + (uint32_t)buf * 256u);
+                        tc5::tmem_ld_32x32b_x32(r[1], taddr0 + (uint32_t)buf * 256u + 32u);
+                        tc5::tmem_ld_wait();
+                        tc5::fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) tc5::mbar_arrive(&ms.tempty[buf]);
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
-                            uint32_t r[32];
-                            tc5::tmem_ld_32x32b_x32(r, taddr0 + (uint32_t)buf * 256u + (uint32_t)half * 32u);
-                            tc5::tmem_ld_wait();
-                            if (half == 1) {  // the accumulator is in registers: hand the buffer back to the MMA issuer
-                                tc5::fence_before_sync();
-                                __syncwarp();
-                                if (lane == 0) tc5::mbar_arrive(&ms.tempty[buf]);
-                            }
+                            // common path: the maximum of each group of 16 cells (3-input max), ONE vote for the 32 cells
+                            const float* v = reinterpret_cast<const float*>(r[half]);
+                            float gm[2];
 #pragma unroll
                             for (int gh = 0; gh < 2; ++gh) {
-                                const float* v = reinterpret_cast<const float*>(r) + 16 * gh;
-                                const float m0 = tc5_max3(v[0], v[1], v[2]), m1 = tc5_max3(v[3], v[4], v[5]);
-                                const float m2 = tc5_max3(v[6], v[7], v[8]), m3 = tc5_max3(v[9], v[10], v[11]);
-                                const float m4 = tc5_max3(v[12], v[13], v[14]);
-                                const float gm = fmaxf(tc5_max3(m0, m1, m2), tc5_max3(m3, m4, v[15]));
-                                const bool hot = gm > thr;
+                                const float* u = v + 16 * gh;
+                                const float m0 = tc5_max3(u[0], u[1], u[2]), m1 = tc5_max3(u[3], u[4], u[5]);
+                                const float m2 = tc5_max3(u[6], u[7], u[8]), m3 = tc5_max3(u[9], u[10], u[11]);
+                                const float m4 = tc5_max3(u[12], u[13], u[14]);
+                                gm[gh] = fmaxf(tc5_max3(m0, m1, m2), tc5_max3(m3, m4, u[15]));
+                            }
+                            if (!__any_sync(SMG_FULL_MASK, fmaxf(gm[0], gm[1]) > thr)) continue;
+                            // ---- rare path: transpose the flagged groups through the scratch and extract the candidates
+#pragma unroll
+                            for (int gh = 0; gh < 2; ++gh) {
+                                const float* u = v + 16 * gh;
+                                const bool hot = gm[gh] > thr;
                                 const unsigned bm = __ballot_sync(SMG_FULL_MASK, hot);
-                                if (bm) {
-                                    // ---- transpose: flagged lanes -> scratch entries, then lane = cell, two entries per ballot
-                                    const int k = __popc(bm);
-                                    if (hot) {
-                                        float4* dst = reinterpret_cast<float4*>(scratch + __popc(bm & lt_mask) * kTc5EntryBytes);
-                                        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-                                        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-                                        dst[2] = make_float4(v[8], v[9], v[10], v[11]);
-                                        dst[3] = make_float4(v[12], v[13], v[14], v[15]);
-                                        reinterpret_cast<uint2*>(dst)[8] = make_uint2(__float_as_uint(thr), (uint32_t)cid);
-                                    }
-                                    __syncwarp();
-                                    const int s0 = t0 + 2 * (colchunk * 64 + (half * 2 + gh) * 16) + e;  // window start of cell 0
-                                    const bool cell_ok = s0 + 2 * cell < c1;                           // starts owned by this chunk
-                                    for (int j = 0; j < k; j += 2) {
-                                        const uint8_t* ent = scratch + (j + sub) * kTc5EntryBytes;
-                                        const uint2 tc = reinterpret_cast<const uint2*>(ent)[8];
-                                        const float val = reinterpret_cast<const float*>(ent)[cell];
-                                        const bool is = cell_ok && (j + sub < k) && (val > __uint_as_float(tc.x));
-                                        const unsigned m = __ballot_sync(SMG_FULL_MASK, is);
-                                        if (m) {
-                                            if (is) {
-                                                const int i = cused + __popc(m & lt_mask);
-                                                const unsigned long long idx = i < kTc5CandBlock ? cbase + i : nbase + (i - kTc5CandBlock);
-                                                if (idx < hp.cand_cap)
-                                                    hp.cand[idx] = rowbits | ((unsigned long long)(unsigned)(s0 + 2 * cell) << pos_shift) |
-                                                                   (unsigned long long)tc.y;
-                                            }
-                                            cused += __popc(m);
-                                            if (cused >= kTc5CandBlock) {  // move on to the reserved block, reserve another one
-                                                cused -= kTc5CandBlock;
-                                                cbase = nbase;
-                                                unsigned long long nb = 0;
-                                                if (lane == 0) nb = atomicAdd(&p.counters[SMG_CTR_CANDIDATES], (unsigned long long)kTc5CandBlock);
-                                                nbase = __shfl_sync(SMG_FULL_MASK, nb, 0);
-                                            }
+                                if (!bm) continue;
+                                const int k = __popc(bm);
+                                if (hot) {
+                                    float4* dst = reinterpret_cast<float4*>(scratch + __popc(bm & lt_mask) * kTc5EntryBytes);
+                                    dst[0] = make_float4(u[0], u[1], u[2], u[3]);
+                                    dst[1] = make_float4(u[4], u[5], u[6], u[7]);
+                                    dst[2] = make_float4(u[8], u[9], u[10], u[11]);
+                                    dst[3] = make_float4(u[12], u[13], u[14], u[15]);
+                                    reinterpret_cast<uint2*>(dst)[8] = make_uint2(__float_as_uint(thr), (uint32_t)hp.col_id[col0 + b * 128]);
+                                }
+                                __syncwarp();
+                                const int s0 = t0 + 2 * (colchunk * 64 + (half * 2 + gh) * 16) + e;  // window start of cell 0
+                                const bool cell_ok = s0 + 2 * cell < c1;                           // starts owned by this chunk
+                                for (int j = 0; j < k; j += 2) {  // lane = cell, two flagged lanes per ballot
+                                    const uint8_t* ent = scratch + (j + sub) * kTc5EntryBytes;
+                                    const uint2 tc = reinterpret_cast<const uint2*>(ent)[8];
+                                    const float val = reinterpret_cast<const float*>(ent)[cell];
+                                    const bool is = cell_ok && (j + sub < k) && (val > __uint_as_float(tc.x));
+                                    const unsigned m = __ballot_sync(SMG_FULL_MASK, is);
+                                    if (m) {
+                                        if (is) {
+                                            const int i = cused + __popc(m & lt_mask);
+                                            const unsigned long long idx = i < kTc5CandBlock ? cbase + i : nbase + (i - kTc5CandBlock);
+                                            if (idx < hp.cand_cap)
+                                                hp.cand[idx] = rowbits | ((unsigned long long)(unsigned)(s0 + 2 * cell) << pos_shift) |
+                                                               (unsigned long long)tc.y;
+                                        }
+                                        cused += __popc(m);
+                                        if (cused >= kTc5CandBlock) {  // move on to the reserved block, reserve another one
+                                            cused -= kTc5CandBlock;
+                                            cbase = nbase;
+                                            unsigned long long nb = 0;
+                                            if (lane == 0) nb = atomicAdd(&p.counters[SMG_CTR_CANDIDATES], (unsigned long long)kTc5CandBlock);
+                                            nbase = __shfl_sync(SMG_FULL_MASK, nb, 0);
                                         }
                                     }
-                                    __syncwarp();  // the scratch is rewritten by the next flagged group
                                 }
+                                __syncwarp();  // the scratch is rewritten by the next flagged group
                             }
                         }
                     }

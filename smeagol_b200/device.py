@@ -501,7 +501,8 @@ class ScanPlan:
                  "n_candidates": int(c[_lib.CTR_CANDIDATES])}
         keys, scores = self.keys, self.scores
         if self.want_hits and sort and n_hits > 0:
-            keys, scores = sort_hits(keys, scores, n_hits, self.key_bits)
+            keys, scores = sort_hits(keys, scores, n_hits, self.key_bits, motif_bits=self.motif_bits,
+                                     total_positions=self.batch.total_own * bin(self.strands).count("1"))
         return ScanResult(keys, scores, n_hits, self.counts, self.pos_bits, self.motif_bits, stats)
 
 
@@ -519,14 +520,38 @@ def scan(pwmset, batch, thr64, strands, out_rows, n_out_rows, want_hits=True, wa
     return plan.finish(sort=sort)
 
 
-def sort_hits(keys, scores, n, key_bits, keys_out=None, scores_out=None, temp=None, return_temp=False):
+def sort_hits(keys, scores, n, key_bits, keys_out=None, scores_out=None, temp=None, return_temp=False, motif_bits=None,
+              n_out_rows=None, total_positions=None, overflow_flag=None):
     """Sort the first n (key, score) pairs into the reference's np.where order.  temp: reusable scratch (grown when too
-    small; pass return_temp=True to get the possibly re-allocated buffer back as a third result)."""
+    small; pass return_temp=True to get the possibly re-allocated buffer back as a third result).
+
+    With motif_bits (and the scan's geometry) the BUCKETED sort is used (csrc/sort_buckets.cu: one scatter pass into
+    (output row, position block) buckets + a shared-memory sort per bucket); if a bucket overflows (extreme local hit
+    density) the call falls back to the radix sort -- one small D2H read of the overflow flag decides."""
     lib = _lib.load()
     dev = keys.device
     if keys_out is None:
         keys_out = torch.empty(n, dtype=torch.int64, device=dev)
         scores_out = torch.empty(n, dtype=torch.float32, device=dev)
+    if motif_bits is not None and 0 < n < (1 << 32) and os.environ.get("SMEAGOL_B200_SORT", "bucket") == "bucket":
+        # positions per bucket: ~1.5 K hits on average (capacity 4,096), at most 2^28 buckets
+        per_pos = n / max(float(total_positions or n), 1.0)
+        b = int(np.clip(np.floor(np.log2(max(1536.0 / max(per_pos, 1e-9), 1.0))), 0, min(11, 31 - motif_bits)))
+        shift = motif_bits + b
+        if key_bits - shift <= 26 and shift < key_bits:
+            tb = ctypes.c_uint64(0)
+            _lib.check(lib.smg_sort_hits_bucketed(_ptr(keys), _ptr(scores), _ptr(keys_out), _ptr(scores_out), n, key_bits, motif_bits, shift,
+                                                  None, ctypes.byref(tb), None, _stream()), "smg_sort_hits_bucketed(query)")
+            if temp is None or temp.numel() < int(tb.value):
+                temp = torch.empty(max(int(tb.value), 16), dtype=torch.uint8, device=dev)
+            if overflow_flag is None:
+                overflow_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            tb = ctypes.c_uint64(temp.numel())
+            _lib.check(lib.smg_sort_hits_bucketed(_ptr(keys), _ptr(scores), _ptr(keys_out), _ptr(scores_out), n, key_bits, motif_bits, shift,
+                                                  _ptr(temp), ctypes.byref(tb), _ptr(overflow_flag), _stream()),
+                       "smg_sort_hits_bucketed")
+            if int(overflow_flag.item()) == 0:
+                return (keys_out, scores_out, temp) if return_temp else (keys_out, scores_out)
     tb = ctypes.c_uint64(0)
     _lib.check(lib.smg_sort_hits(_ptr(keys), _ptr(scores), _ptr(keys_out), _ptr(scores_out), n, key_bits, None,
                                  ctypes.byref(tb), _stream()), "smg_sort_hits(query)")

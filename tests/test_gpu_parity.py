@@ -387,6 +387,38 @@ def test_benchmark_slice_full_parity_vs_c_oracle():
     assert res.stats["n_near"] >= exp["n_near"]  # the kernel's fp32 band is a superset of the oracle's fp64 band
 
 
+def test_bucketed_sort_equals_radix_sort(monkeypatch):
+    """csrc/sort_buckets.cu (scatter into (row, position block) buckets + shared-memory sort per bucket) against
+    cub::DeviceRadixSort on the same unsorted hit lists: many rows, one long row, a hit-dense low-complexity stretch that
+    overflows a bucket (the call must fall back, never truncate), tiny inputs."""
+    import torch
+
+    sb = _sb()
+    from smeagol_b200 import device as dev
+
+    rng = np.random.default_rng(59)
+    model = sb.models.PWMModel(synth_pwms(rng, 120, 6, 14))
+    cases = [[rand_seq(rng, int(n)) for n in rng.integers(50, 4000, size=40)], [rand_seq(rng, 300_000)],
+             [rand_seq(rng, 20_000) + "A" * 30_000 + rand_seq(rng, 20_000)], ["ACGTACGTAC"], [rand_seq(rng, 64)]]
+    for seqs in cases:
+        n = len(seqs)
+        batch = dev.SeqBatch(seqs)
+        out_rows = np.stack([np.arange(n), n + np.arange(n)], axis=1).astype(np.int32)
+        plan = dev.ScanPlan(model.device_set, batch, model.thresholds(0.55), 3, out_rows, 2 * n)
+        plan.launch()
+        res = plan.finish(sort=False)
+        if res.n_hits == 0:
+            continue
+        monkeypatch.setenv("SMEAGOL_B200_SORT", "radix")
+        k0, s0 = dev.sort_hits(res.keys, res.scores, res.n_hits, plan.key_bits)
+        monkeypatch.setenv("SMEAGOL_B200_SORT", "bucket")
+        k1, s1 = dev.sort_hits(res.keys, res.scores, res.n_hits, plan.key_bits, motif_bits=plan.motif_bits,
+                               total_positions=2 * batch.total_own)
+        assert torch.equal(k0, k1) and torch.equal(s0.view(torch.int32), s1.view(torch.int32))
+        assert bool((k1[1:] > k1[:-1]).all().item()) if res.n_hits > 1 else True
+    monkeypatch.delenv("SMEAGOL_B200_SORT")
+
+
 def test_buffer_overflow_is_detected_and_retried():
     """Hit / near-threshold buffers that are too small are regrown and the scan repeated -- never truncated."""
     sb = _sb()
