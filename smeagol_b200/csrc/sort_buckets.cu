@@ -4,7 +4,7 @@
 // far from random, though: a hit's high bits are (output row, position) and the scan engines emit hits chunk by chunk.
 // So: (1) histogram of the hits over BUCKETS = key >> (motif_bits + B) (one output row x 2^B positions each, sized on
 // the host for ~1-2 K hits), (2) exclusive scan, (3) ONE scatter pass that moves every hit into its bucket as a 32-bit
-// (position-in-bucket, motif) key + score, (4) one CTA per bucket orders its hits in shared memory (counting sort over the
+// (position-in-bucket, motif) key + score, (4) one WARP per bucket orders its hits in shared memory (counting sort over the
 // 2^B positions + insertion sort by motif inside a position) and writes the final 64-bit keys and scores.  48 B of DRAM
 // traffic per hit instead of 128.
 // Warps aggregate their bucket-counter atomics with __match_any_sync: 32 consecutive hits of the unsorted list come
@@ -12,7 +12,6 @@
 // radix sort for that call); nothing is ever truncated.
 #include <string>
 
-#include <cub/block/block_scan.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
@@ -22,10 +21,9 @@ void smg_count_launch();
 
 namespace smg {
 
-constexpr int kSortThreads = 256;
-constexpr int kSortItems = 16;
-constexpr int kSortCap = kSortThreads * kSortItems;  // hits a bucket may hold
-constexpr int kSortMaxBins = 2048;                   // positions a bucket may span (2^11)
+constexpr int kSortThreads = 128;  // 4 warps = 4 buckets in flight per CTA (41 KB of shared memory: 5 CTAs per SM)
+constexpr int kSortCap = 1024;     // hits a bucket may hold (one warp orders a bucket in shared memory)
+constexpr int kSortMaxBins = 512;  // positions a bucket may span (2^9)
 
 __global__ void __launch_bounds__(256) bucket_hist_kernel(const unsigned long long* __restrict__ keys, const unsigned long long n,
                                                           const int shift, unsigned* __restrict__ counts)
@@ -68,93 +66,94 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(const unsigned long
 }
 
 // offsets[b] .. offsets[b + 1]: the bucket's hits in `low` / `sc`; output at the same offsets of keys_out / scores_out.
-// A bucket spans 2^pb positions of one output row, so its hits are ordered with ONE counting sort over the position
-// (shared-memory histogram, block scan, scatter) followed by an insertion sort of the few hits that share a position
-// (ordered by motif): ~30 instructions per hit, against ~240 for a 22-bit block radix sort.
+// ONE WARP PER BUCKET (no block-wide barriers, 8 independent warps per CTA): a bucket spans 2^pb <= 512 positions of one
+// output row, so its hits are ordered with one counting sort over the position (shared-memory histogram, warp scan,
+// scatter) followed by an insertion sort of the few hits that share a position (ordered by motif): ~30 instructions per
+// hit, against ~240 for a 22-bit block radix sort.
 __global__ void __launch_bounds__(kSortThreads) bucket_sort_kernel(const unsigned* __restrict__ offsets, const unsigned n_buckets,
                                                                    const uint32_t* __restrict__ low, const float* __restrict__ sc,
                                                                    const int shift, const int motif_bits,
                                                                    unsigned long long* __restrict__ keys_out,
                                                                    float* __restrict__ scores_out, unsigned* __restrict__ overflow)
 {
-    using Scan = cub::BlockScan<unsigned, kSortThreads>;
-    __shared__ typename Scan::TempStorage scan_tmp;
-    __shared__ uint32_t s_low[kSortCap];
-    __shared__ float s_sc[kSortCap];
-    __shared__ unsigned s_cnt[kSortMaxBins + 1];
-    const int tid = threadIdx.x;
+    constexpr int kWarps = kSortThreads / 32;
+    __shared__ uint32_t s_low[kWarps][kSortCap];
+    __shared__ float s_sc[kWarps][kSortCap];
+    __shared__ unsigned s_cnt[kWarps][kSortMaxBins + 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* wl = s_low[warp];
+    float* ws = s_sc[warp];
+    unsigned* cnt = s_cnt[warp];
     const int n_bins = 1 << (shift - motif_bits);
-    constexpr int kBinsPerThread = kSortMaxBins / kSortThreads;
-    for (unsigned b = blockIdx.x; b < n_buckets; b += gridDim.x) {
+    constexpr int kPer = kSortMaxBins / 32;  // bins per lane in the scan
+    for (unsigned b = blockIdx.x * kWarps + warp; b < n_buckets; b += gridDim.x * kWarps) {
         const unsigned o0 = offsets[b], n = offsets[b + 1] - o0;
         if (n == 0) continue;
         if (n > (unsigned)kSortCap) {  // reported, handled by the caller
-            if (tid == 0) atomicAdd(overflow, 1u);
+            if (lane == 0) atomicAdd(overflow, 1u);
             continue;
         }
-        for (int i = tid; i <= n_bins; i += kSortThreads) s_cnt[i] = 0u;
-        __syncthreads();
-        uint32_t k[kSortItems];
-        float v[kSortItems];
-        unsigned rnk[kSortItems];
-#pragma unroll
-        for (int i = 0; i < kSortItems; ++i) {
-            const unsigned j = (unsigned)i * kSortThreads + tid;
-            if (j < n) {
-                k[i] = low[o0 + j];
-                v[i] = sc[o0 + j];
-                rnk[i] = atomicAdd(&s_cnt[k[i] >> motif_bits], 1u);
+        if (n == 1) {
+            if (lane == 0) {
+                keys_out[o0] = ((unsigned long long)b << shift) | low[o0];
+                scores_out[o0] = sc[o0];
             }
+            continue;
         }
-        __syncthreads();
-        // exclusive scan of the per-position counts (kBinsPerThread consecutive bins per thread)
-        unsigned c[kBinsPerThread];
+        for (int i = lane; i < kSortMaxBins + 32; i += 32) cnt[i] = 0u;
+        __syncwarp();
+        for (unsigned j = lane; j < n; j += 32) atomicAdd(&cnt[low[o0 + j] >> motif_bits], 1u);
+        __syncwarp();
+        // exclusive scan of the per-position counts: kPer consecutive bins per lane, then a warp scan of the lane totals
+        unsigned c[kPer], tot = 0;
 #pragma unroll
-        for (int i = 0; i < kBinsPerThread; ++i) {
-            const int bin = tid * kBinsPerThread + i;
-            c[i] = bin < n_bins ? s_cnt[bin] : 0u;
+        for (int i = 0; i < kPer; ++i) {
+            c[i] = cnt[lane * kPer + i];
+            tot += c[i];
         }
-        Scan(scan_tmp).ExclusiveSum(c, c);
-        __syncthreads();
+        unsigned incl = tot;
 #pragma unroll
-        for (int i = 0; i < kBinsPerThread; ++i) {
-            const int bin = tid * kBinsPerThread + i;
-            if (bin < n_bins) s_cnt[bin] = c[i];
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(SMG_FULL_MASK, incl, d);
+            if (lane >= d) incl += t;
         }
-        if (tid == 0) s_cnt[n_bins] = n;
-        __syncthreads();
+        unsigned run = incl - tot;
+        __syncwarp();
 #pragma unroll
-        for (int i = 0; i < kSortItems; ++i) {
-            const unsigned j = (unsigned)i * kSortThreads + tid;
-            if (j < n) {
-                const unsigned slot = s_cnt[k[i] >> motif_bits] + rnk[i];
-                s_low[slot] = k[i];
-                s_sc[slot] = v[i];
-            }
+        for (int i = 0; i < kPer; ++i) {
+            cnt[lane * kPer + i] = run;  // start of the bin; advanced by the scatter below, so it ends as the bin's END
+            run += c[i];
         }
-        __syncthreads();
-        // hits sharing a position: order by motif (a handful at most)
-        for (int bin = tid; bin < n_bins; bin += kSortThreads) {
-            const unsigned lo = s_cnt[bin], hi = s_cnt[bin + 1];
+        __syncwarp();
+        for (unsigned j = lane; j < n; j += 32) {
+            const uint32_t k = low[o0 + j];
+            const unsigned slot = atomicAdd(&cnt[k >> motif_bits], 1u);
+            wl[slot] = k;
+            ws[slot] = sc[o0 + j];
+        }
+        __syncwarp();
+        // hits sharing a position: order by motif (a handful at most).  cnt[bin] is now the END of bin, cnt[bin - 1] its start.
+        for (int bin = lane; bin < n_bins; bin += 32) {
+            const unsigned hi = cnt[bin], lo = bin ? cnt[bin - 1] : 0u;
             for (unsigned x = lo + 1; x < hi; ++x) {
-                const uint32_t kk = s_low[x];
-                const float vv = s_sc[x];
+                const uint32_t kk = wl[x];
+                const float vv = ws[x];
                 unsigned y = x;
-                while (y > lo && s_low[y - 1] > kk) {
-                    s_low[y] = s_low[y - 1];
-                    s_sc[y] = s_sc[y - 1];
+                while (y > lo && wl[y - 1] > kk) {
+                    wl[y] = wl[y - 1];
+                    ws[y] = ws[y - 1];
                     --y;
                 }
-                s_low[y] = kk;
-                s_sc[y] = vv;
+                wl[y] = kk;
+                ws[y] = vv;
             }
         }
-        __syncthreads();
-        for (unsigned j = tid; j < n; j += kSortThreads) {
-            keys_out[o0 + j] = ((unsigned long long)b << shift) | s_low[j];
-            scores_out[o0 + j] = s_sc[j];
+        __syncwarp();
+        for (unsigned j = lane; j < n; j += 32) {
+            keys_out[o0 + j] = ((unsigned long long)b << shift) | wl[j];
+            scores_out[o0 + j] = ws[j];
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -167,7 +166,7 @@ int smg_sort_hits_bucketed(const uint64_t* d_keys_in, const float* d_scores_in, 
                            void* stream)
 {
     if (!temp_bytes || key_bits <= 0 || key_bits > 63 || bucket_shift <= 0 || bucket_shift > 31 || bucket_shift >= key_bits || motif_bits <= 0 || motif_bits > bucket_shift ||
-        bucket_shift - motif_bits > 11 ||
+        bucket_shift - motif_bits > 9 ||
         key_bits - bucket_shift > 28 || n >= (1ull << 32))
         return smg_fail_from(SMG_ERR_INVALID, "smg_sort_hits_bucketed: bad argument");
     const uint64_t n_buckets = 1ull << (key_bits - bucket_shift);
@@ -205,7 +204,7 @@ int smg_sort_hits_bucketed(const uint64_t* d_keys_in, const float* d_scores_in, 
     smg::bucket_scatter_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(d_keys_in), d_scores_in, n,
                                                        bucket_shift, counts, low, sc);
     smg_count_launch();
-    const unsigned sblocks = (unsigned)std::min<uint64_t>(n_buckets, 148 * 64);
+    const unsigned sblocks = (unsigned)std::min<uint64_t>((n_buckets + 3) / 4, 148 * 80);
     smg::bucket_sort_kernel<<<sblocks, smg::kSortThreads, 0, st>>>(offsets, (unsigned)n_buckets, low, sc, bucket_shift, motif_bits,
                                                                    reinterpret_cast<unsigned long long*>(d_keys_out), d_scores_out,
                                                                    d_overflow);

@@ -534,9 +534,9 @@ def sort_hits(keys, scores, n, key_bits, keys_out=None, scores_out=None, temp=No
         keys_out = torch.empty(n, dtype=torch.int64, device=dev)
         scores_out = torch.empty(n, dtype=torch.float32, device=dev)
     if motif_bits is not None and 0 < n < (1 << 32) and os.environ.get("SMEAGOL_B200_SORT", "bucket") == "bucket":
-        # positions per bucket: ~1.5 K hits on average (capacity 4,096), at most 2^28 buckets
+        # positions per bucket: ~300-400 hits on average (a warp orders up to 1,024 in shared memory), at most 2^26 buckets
         per_pos = n / max(float(total_positions or n), 1.0)
-        b = int(np.clip(np.floor(np.log2(max(1536.0 / max(per_pos, 1e-9), 1.0))), 0, min(11, 31 - motif_bits)))
+        b = int(np.clip(np.floor(np.log2(max(384.0 / max(per_pos, 1e-9), 1.0))), 0, min(9, 31 - motif_bits)))
         shift = motif_bits + b
         if key_bits - shift <= 26 and shift < key_bits:
             tb = ctypes.c_uint64(0)
