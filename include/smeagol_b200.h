@@ -242,8 +242,7 @@ int smg_sort_hits(const uint64_t* d_keys_in, const float* d_scores_in, uint64_t*
 /* The same order, bucketed (smeagol_b200/csrc/sort_buckets.cu): one scatter pass moves every hit into its bucket
  * key >> bucket_shift (an output row x a block of positions; bucket_shift = motif_bits + log2(positions per bucket) <= 31,
  * at most 2^9 positions per bucket and 2^28 buckets), then every bucket is ordered in shared memory.  48 B of DRAM traffic per hit instead of the radix
- * sort's 128.  *d_overflow (device uint32) = number of buckets holding more than 1,024 hits: if non-zero the outputs are
- * incomplete and the caller must fall back to smg_sort_hits (or retry with a smaller bucket_shift).  n < 2^32.
+ * sort's 128.  *d_overflow (device uint32): reserved, always written as 0 (a bucket may hold any number of hits).  n < 2^32.
  * Call with d_temp == NULL to query *temp_bytes. */
 int smg_sort_hits_bucketed(const uint64_t* d_keys_in, const float* d_scores_in, uint64_t* d_keys_out, float* d_scores_out,
                            uint64_t n, int key_bits, int motif_bits, int bucket_shift, void* d_temp, uint64_t* temp_bytes,

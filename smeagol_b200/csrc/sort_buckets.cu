@@ -8,8 +8,8 @@
 // 2^B positions + insertion sort by motif inside a position) and writes the final 64-bit keys and scores.  48 B of DRAM
 // traffic per hit instead of 128.
 // Warps aggregate their bucket-counter atomics with __match_any_sync: 32 consecutive hits of the unsorted list come
-// from one or two chunks.  A bucket that exceeds the CTA's capacity is reported to the caller (which falls back to the
-// radix sort for that call); nothing is ever truncated.
+// from one or two chunks.  A bucket may hold any number of hits (only its per-position counters live in shared memory);
+// *d_overflow is kept in the interface and always reports 0.
 #include <string>
 
 #include <cub/device/device_scan.cuh>
@@ -21,8 +21,7 @@ void smg_count_launch();
 
 namespace smg {
 
-constexpr int kSortThreads = 128;  // 4 warps = 4 buckets in flight per CTA (41 KB of shared memory: 5 CTAs per SM)
-constexpr int kSortCap = 1024;     // hits a bucket may hold (one warp orders a bucket in shared memory)
+constexpr int kSortThreads = 256;  // 8 warps = 8 buckets in flight per CTA
 constexpr int kSortMaxBins = 512;  // positions a bucket may span (2^9)
 
 __global__ void __launch_bounds__(256) bucket_hist_kernel(const unsigned long long* __restrict__ keys, const unsigned long long n,
@@ -66,36 +65,29 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(const unsigned long
 }
 
 // offsets[b] .. offsets[b + 1]: the bucket's hits in `low` / `sc`; output at the same offsets of keys_out / scores_out.
-// ONE WARP PER BUCKET (no block-wide barriers, 8 independent warps per CTA): a bucket spans 2^pb <= 512 positions of one
-// output row, so its hits are ordered with one counting sort over the position (shared-memory histogram, warp scan,
-// scatter) followed by an insertion sort of the few hits that share a position (ordered by motif): ~30 instructions per
-// hit, against ~240 for a 22-bit block radix sort.
+// ONE WARP PER BUCKET (no block-wide barriers, 8 independent warps per CTA, 2 KB of shared memory each): a bucket spans
+// 2^pb <= 512 positions of one output row, so its hits are ordered with one counting sort over the position (shared-memory
+// histogram, warp scan, scatter straight to the final arrays) followed by an insertion sort of the few hits that share a
+// position (ordered by motif, in place in global memory): ~30 instructions per hit, against ~240 for a block radix sort.
 __global__ void __launch_bounds__(kSortThreads) bucket_sort_kernel(const unsigned* __restrict__ offsets, const unsigned n_buckets,
                                                                    const uint32_t* __restrict__ low, const float* __restrict__ sc,
                                                                    const int shift, const int motif_bits,
                                                                    unsigned long long* __restrict__ keys_out,
-                                                                   float* __restrict__ scores_out, unsigned* __restrict__ overflow)
+                                                                   float* __restrict__ scores_out)
 {
     constexpr int kWarps = kSortThreads / 32;
-    __shared__ uint32_t s_low[kWarps][kSortCap];
-    __shared__ float s_sc[kWarps][kSortCap];
     __shared__ unsigned s_cnt[kWarps][kSortMaxBins + 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* wl = s_low[warp];
-    float* ws = s_sc[warp];
     unsigned* cnt = s_cnt[warp];
     const int n_bins = 1 << (shift - motif_bits);
     constexpr int kPer = kSortMaxBins / 32;  // bins per lane in the scan
     for (unsigned b = blockIdx.x * kWarps + warp; b < n_buckets; b += gridDim.x * kWarps) {
         const unsigned o0 = offsets[b], n = offsets[b + 1] - o0;
         if (n == 0) continue;
-        if (n > (unsigned)kSortCap) {  // reported, handled by the caller
-            if (lane == 0) atomicAdd(overflow, 1u);
-            continue;
-        }
+        const unsigned long long hi_bits = (unsigned long long)b << shift;
         if (n == 1) {
             if (lane == 0) {
-                keys_out[o0] = ((unsigned long long)b << shift) | low[o0];
+                keys_out[o0] = hi_bits | low[o0];
                 scores_out[o0] = sc[o0];
             }
             continue;
@@ -128,30 +120,28 @@ __global__ void __launch_bounds__(kSortThreads) bucket_sort_kernel(const unsigne
         for (unsigned j = lane; j < n; j += 32) {
             const uint32_t k = low[o0 + j];
             const unsigned slot = atomicAdd(&cnt[k >> motif_bits], 1u);
-            wl[slot] = k;
-            ws[slot] = sc[o0 + j];
+            keys_out[o0 + slot] = hi_bits | k;
+            scores_out[o0 + slot] = sc[o0 + j];
         }
-        __syncwarp();
+        __syncwarp();  // orders the stores above before the reads below (same warp)
         // hits sharing a position: order by motif (a handful at most).  cnt[bin] is now the END of bin, cnt[bin - 1] its start.
         for (int bin = lane; bin < n_bins; bin += 32) {
             const unsigned hi = cnt[bin], lo = bin ? cnt[bin - 1] : 0u;
+            if (hi - lo < 2) continue;
+            unsigned long long* kp = keys_out + o0;
+            float* sp = scores_out + o0;
             for (unsigned x = lo + 1; x < hi; ++x) {
-                const uint32_t kk = wl[x];
-                const float vv = ws[x];
+                const unsigned long long kk = kp[x];
+                const float vv = sp[x];
                 unsigned y = x;
-                while (y > lo && wl[y - 1] > kk) {
-                    wl[y] = wl[y - 1];
-                    ws[y] = ws[y - 1];
+                while (y > lo && kp[y - 1] > kk) {
+                    kp[y] = kp[y - 1];
+                    sp[y] = sp[y - 1];
                     --y;
                 }
-                wl[y] = kk;
-                ws[y] = vv;
+                kp[y] = kk;
+                sp[y] = vv;
             }
-        }
-        __syncwarp();
-        for (unsigned j = lane; j < n; j += 32) {
-            keys_out[o0 + j] = ((unsigned long long)b << shift) | wl[j];
-            scores_out[o0 + j] = ws[j];
         }
         __syncwarp();
     }
@@ -204,10 +194,9 @@ int smg_sort_hits_bucketed(const uint64_t* d_keys_in, const float* d_scores_in, 
     smg::bucket_scatter_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(d_keys_in), d_scores_in, n,
                                                        bucket_shift, counts, low, sc);
     smg_count_launch();
-    const unsigned sblocks = (unsigned)std::min<uint64_t>((n_buckets + 3) / 4, 148 * 80);
+    const unsigned sblocks = (unsigned)std::min<uint64_t>((n_buckets + 7) / 8, 148 * 64);
     smg::bucket_sort_kernel<<<sblocks, smg::kSortThreads, 0, st>>>(offsets, (unsigned)n_buckets, low, sc, bucket_shift, motif_bits,
-                                                                   reinterpret_cast<unsigned long long*>(d_keys_out), d_scores_out,
-                                                                   d_overflow);
+                                                                   reinterpret_cast<unsigned long long*>(d_keys_out), d_scores_out);
     smg_count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return smg_fail_from(SMG_ERR_CUDA, std::string("bucket sort kernels: ") + cudaGetErrorString(e));
