@@ -260,11 +260,24 @@ int smg_variant_sites(smg_pwmset_t set, const uint32_t* d_packed, const uint16_t
                       const int32_t* d_site_motif, const int32_t* d_rel_pos, const uint8_t* d_alt_code, int64_t n,
                       double* d_out_ref, double* d_out_alt, void* stream);
 
-/* BASELINE config 5 (batched restatement of variant.py): for every SNV (row, pos, alt) and every PWM, the maximum
- * reference and alternate score over all windows covering pos on both strands (fp32).  Outputs [n_snv][n_motifs]. */
+/* BASELINE config 5 (batched restatement of variant.py:7-47 + scan.py:8-37): for every SNV (row, pos, alt) and every
+ * PWM, the maximum reference and alternate score over all windows covering pos on both strands (fp32).  Outputs
+ * [n_snv][n_motifs].  Every score is the fixed ascending-k fp32 sum (bit-identical to the CPU restatement). */
 int smg_variant_windows(smg_pwmset_t set, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
                         const smg_row_t* d_rows, const int32_t* d_snv_row, const int32_t* d_snv_pos,
                         const uint8_t* d_snv_alt, int64_t n_snv, float* d_ref_max, float* d_alt_max, void* stream);
+
+/* Same, with the choice of how alternate scores are formed and of the output layout.  motif_major = 0: outputs
+ * [n_snv][n_motifs] as above; motif_major = 1: outputs [n_motifs][n_snv] -- the layout the kernels write as whole
+ * 128-byte lines (the SNV-major layout costs ~8x the DRAM traffic: partial sectors that the L2 reads back).
+ * exact = 1: alternate scores as smg_variant_windows.  exact = 0: the
+ * alternate score of a window is (reference score - T[k][ref base]) + T[k][alt base] (k = offset of the SNV in the
+ * window) -- the reference maxima are unchanged, alternate scores may differ from the fresh sum by a few ulp of the
+ * largest partial sum (<= 1e-5 * sum_k max_b |T[k][b]|); falls back to exact = 1 when a table holds a non-finite entry. */
+int smg_variant_windows_mode(smg_pwmset_t set, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
+                             const smg_row_t* d_rows, const int32_t* d_snv_row, const int32_t* d_snv_pos,
+                             const uint8_t* d_snv_alt, int64_t n_snv, float* d_ref_max, float* d_alt_max, int32_t exact,
+                             int32_t motif_major, void* stream);
 
 #ifdef __cplusplus
 }

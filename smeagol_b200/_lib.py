@@ -20,7 +20,7 @@ EXPORTS = [
     "smg_version", "smg_last_error", "smg_launch_count", "smg_pwmset_create", "smg_pwmset_create_split", "smg_pwmset_create_split3",
     "smg_kmer_index_size", "smg_kmer_index_build", "smg_scan_kmer", "smg_pwmset_destroy", "smg_pwmset_info",
     "smg_pack", "smg_scan", "smg_scan_tc", "smg_scan_tc5", "smg_adjudicate", "smg_sort_hits", "smg_sort_hits_bucketed", "smg_predict_dense", "smg_variant_sites",
-    "smg_variant_windows", "smg_pairwise_ncorrs", "smg_window_counts", "smg_fasta_index", "smg_fasta_compact", "smg_kmer_shuffle", "smg_bin_hits",
+    "smg_variant_windows", "smg_variant_windows_mode", "smg_pairwise_ncorrs", "smg_window_counts", "smg_fasta_index", "smg_fasta_compact", "smg_kmer_shuffle", "smg_bin_hits",
 ]
 
 
@@ -72,6 +72,7 @@ def load():
     lib.smg_predict_dense.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp]
     lib.smg_variant_sites.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp]
     lib.smg_variant_windows.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp]
+    lib.smg_variant_windows_mode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("smg_version", "smg_last_error", "smg_launch_count"):

@@ -58,6 +58,7 @@ struct Bucket {
     int n_groups;
 };
 struct smg_pwmset {
+    bool all_finite = true;  // no +-inf / NaN table entry (the delta form of the SNV kernel needs that)
     int n_motifs = 0;
     int max_w = 0;
     std::vector<int> widths;
@@ -303,7 +304,9 @@ __global__ void __launch_bounds__(128) variant_windows_kernel(const ScanParams p
                                                               const int32_t* __restrict__ snv_pos, const uint8_t* __restrict__ snv_alt,
                                                               const int64_t n_snv, float* __restrict__ ref_max, float* __restrict__ alt_max,
                                                               const int32_t* __restrict__ motif_list, const int n_list,
-                                                              const unsigned int* __restrict__ flags)
+                                                              const unsigned int* __restrict__ slow_list,
+                                                              const unsigned int* __restrict__ slow_count,
+                                                              const int64_t snv_stride, const int64_t motif_stride)
 {
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
@@ -313,8 +316,10 @@ __global__ void __launch_bounds__(128) variant_windows_kernel(const ScanParams p
     const int wm = active ? p.motif_width[m] : 0;
     const float* tab = active ? p.nat_tab + p.motif_off[m] * 4 : nullptr;
     const float ninf = __int_as_float(0xff800000);
-    for (int64_t v = (int64_t)blockIdx.x * 4 + warp_in_block; v < n_snv; v += (int64_t)gridDim.x * 4) {
-        if (flags != nullptr && flags[v] == 0u) continue;
+    // slow_list != nullptr: only the SNVs the register-table kernels could not take (usually none: the grid exits at once)
+    const int64_t n_todo = slow_list ? (int64_t)*slow_count : n_snv;
+    for (int64_t vi = (int64_t)blockIdx.x * 4 + warp_in_block; vi < n_todo; vi += (int64_t)gridDim.x * 4) {
+        const int64_t v = slow_list ? (int64_t)slow_list[vi] : vi;
         const smg_row_t row = p.rows[snv_row[v]];
         const int64_t pos = snv_pos[v];
         const int alt = snv_alt[v] <= 16 ? snv_alt[v] : 0;
@@ -339,8 +344,8 @@ __global__ void __launch_bounds__(128) variant_windows_kernel(const ScanParams p
                     amax = fmaxf(amax, aa);
                 }
             }
-            ref_max[v * p.n_motifs + m] = rmax;
-            alt_max[v * p.n_motifs + m] = amax;
+            ref_max[v * snv_stride + m * motif_stride] = rmax;
+            alt_max[v * snv_stride + m * motif_stride] = amax;
         }
     }
 }
@@ -543,6 +548,8 @@ int smg_pwmset_create_split3(const float* h_weights, const int32_t* h_widths, in
         tot += h_widths[m];
         s->max_w = std::max(s->max_w, (int)h_widths[m]);
     }
+    s->all_finite = true;
+    for (int64_t i = 0; i < tot * 4; ++i) s->all_finite = s->all_finite && std::isfinite(h_weights[i]);
     // Non-finite weights (log2 of a zero probability) are stored as given.  The reference's one-hot contraction turns
     // every window of such a PWM into NaN (never a hit); the kernels add the selected weight only, so the caller
     // reproduces that by passing +inf thresholds for these PWMs (smeagol_b200/device.py does).
@@ -1157,10 +1164,20 @@ int smg_variant_windows(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t
                         const smg_row_t* d_rows, const int32_t* d_snv_row, const int32_t* d_snv_pos, const uint8_t* d_snv_alt,
                         int64_t n_snv, float* d_ref_max, float* d_alt_max, void* stream)
 {
+    return smg_variant_windows_mode(s, d_packed, d_amask, d_codes, d_rows, d_snv_row, d_snv_pos, d_snv_alt, n_snv, d_ref_max,
+                                    d_alt_max, 1, 0, stream);
+}
+
+int smg_variant_windows_mode(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
+                             const smg_row_t* d_rows, const int32_t* d_snv_row, const int32_t* d_snv_pos,
+                             const uint8_t* d_snv_alt, int64_t n_snv, float* d_ref_max, float* d_alt_max, int32_t exact,
+                             int32_t motif_major, void* stream)
+{
     if (!s || !d_packed || !d_amask || !d_rows || !d_snv_row || !d_snv_pos || !d_snv_alt || n_snv < 0 || !d_ref_max || !d_alt_max)
         return fail(SMG_ERR_INVALID, "smg_variant_windows: bad argument");
     if (n_snv == 0) return SMG_OK;
     if (s->kmin > 1) return fail(SMG_ERR_INVALID, "smg_variant_windows: needs a PWM set built without a k-mer split");
+    const int64_t snv_stride = motif_major ? 1 : (int64_t)s->n_motifs, motif_stride = motif_major ? n_snv : 1;
     ScanParams p;
     fill_params(p, s, d_packed, d_amask, d_codes, d_rows, nullptr);
     cudaStream_t st = (cudaStream_t)stream;
@@ -1169,12 +1186,16 @@ int smg_variant_windows(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t
     // in the region, ambiguous alt) are flagged and redone by the generic kernel, as are the wider PWMs.
     unsigned int* d_flags = nullptr;
     if (!s->dual_motifs.empty()) {
-        SMG_CUDA(cudaMallocAsync((void**)&d_flags, (size_t)n_snv * sizeof(unsigned int), st));
-        SMG_CUDA(cudaMemsetAsync(d_flags, 0, (size_t)n_snv * sizeof(unsigned int), st));
+        // [n_snv] flags | [n_snv] list of flagged SNVs | count
+        SMG_CUDA(cudaMallocAsync((void**)&d_flags, (size_t)(2 * n_snv + 1) * sizeof(unsigned int), st));
+        SMG_CUDA(cudaMemsetAsync(d_flags, 0, (size_t)(2 * n_snv + 1) * sizeof(unsigned int), st));
         smg::VariantParams vp;
         vp.sp = p; vp.snv_row = d_snv_row; vp.snv_pos = d_snv_pos; vp.snv_alt = d_snv_alt; vp.n_snv = n_snv;
         vp.ref_max = d_ref_max; vp.alt_max = d_alt_max; vp.slow_flags = d_flags;
-        const int blocks = (int)std::min<int64_t>(n_snv, 148 * 16 * 4);
+        vp.slow_list = d_flags + n_snv; vp.slow_count = d_flags + 2 * n_snv;
+        vp.exact = (exact || !s->all_finite) ? 1 : 0;
+        vp.snv_stride = snv_stride; vp.motif_stride = motif_stride;
+        const int blocks = (int)std::min<int64_t>((n_snv + 31) / 32, 148 * 16 * 4);  // a CTA (one warp) takes 32 SNVs at a time
         for (const Bucket& b : s->buckets) {
             smg_variant_launch_fn fn = smg_get_variant_launcher(b.wb);
             if (!fn) return fail(SMG_ERR_INVALID, "smg_variant_windows: no kernel for padded width " + std::to_string(b.wb));
@@ -1184,14 +1205,16 @@ int smg_variant_windows(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t
         }
         dim3 gridf(nb, (unsigned)((s->dual_motifs.size() + 31) / 32), 1);
         variant_windows_kernel<<<gridf, 128, 0, st>>>(p, d_snv_row, d_snv_pos, d_snv_alt, n_snv, d_ref_max, d_alt_max,
-                                                       s->d_dual_list, (int)s->dual_motifs.size(), d_flags);
+                                                       s->d_dual_list, (int)s->dual_motifs.size(), d_flags + n_snv, d_flags + 2 * n_snv,
+                                                       snv_stride, motif_stride);
         SMG_LAUNCH_CHECK("variant_windows_kernel(flagged)");
         SMG_CUDA(cudaFreeAsync(d_flags, st));
     }
     if (!s->nondual_motifs.empty()) {
         dim3 grid(nb, (unsigned)((s->nondual_motifs.size() + 31) / 32), 1);
         variant_windows_kernel<<<grid, 128, 0, st>>>(p, d_snv_row, d_snv_pos, d_snv_alt, n_snv, d_ref_max, d_alt_max,
-                                                      s->d_nondual_list, (int)s->nondual_motifs.size(), nullptr);
+                                                      s->d_nondual_list, (int)s->nondual_motifs.size(), nullptr, nullptr, snv_stride,
+                                                      motif_stride);
         SMG_LAUNCH_CHECK("variant_windows_kernel");
     }
     return SMG_OK;

@@ -1,10 +1,13 @@
-// Batched SNV scoring kernel (BASELINE config 5; batched restatement of smeagol/variant.py:7-47, scan.py:8-37).
+// Batched SNV scoring kernels (BASELINE config 5; batched restatement of smeagol/variant.py:7-47, scan.py:8-37).
 //
 // For every SNV (row, pos, alt) and every PWM: over all windows that cover `pos` on both strands and lie inside the
 // sequence, the maximum reference score and the maximum alternate score.  Same machinery as the fused scan kernel:
-// one warp per CTA, lane = PWM with both strands' tables in registers, the 2*WB-1 bases around the SNV are the
-// warp-uniform operand, window sums advance as a FADD2 shift register (ascending-k order).  Two passes per SNV
-// (reference bases, then the same bases with the SNV position replaced by the alternate base).
+// one warp per CTA, lane = PWM with both strands' tables in registers (packed fp32 pairs), the 2*WB-1 bases around the
+// SNV are the warp-uniform operand.
+//   variant_tri_kernel<WB, FORK>   padded widths <= 16: fully unrolled triangle of window sums, alternate scores either
+//                                  forked from the reference sums (exact) or formed as ref - T[k][ref] + T[k][alt]
+//   variant_regtab_kernel<WB>      padded widths 17..32: the scan kernel's shift register, two passes (ref, alt)
+// SNVs with ambiguity codes nearby are appended to a list and redone by the generic kernel in api.cu.
 #pragma once
 #include "scan_regtab.cuh"
 
@@ -19,6 +22,10 @@ struct VariantParams {
     float* ref_max;
     float* alt_max;
     unsigned int* slow_flags;  // [n_snv] set when the SNV needs the generic path (ambiguity codes in the region)
+    unsigned int* slow_list;   // [n_snv] the flagged SNVs, each once
+    unsigned int* slow_count;  // number of entries of slow_list
+    long long snv_stride, motif_stride;  // element (v, m) of ref_max / alt_max lives at v * snv_stride + m * motif_stride
+    int exact;                 // 1: alternate sums forked from the reference sums (bit-identical to a fresh sum); 0: delta
 };
 
 #define SMG_VSTEP(B, O)                                                                       \
@@ -53,7 +60,8 @@ __global__ void __launch_bounds__(32) variant_regtab_kernel(const VariantParams 
         unsigned long long lo = 0, hi = 0;
         bool slow = (alt < 1 || alt > 5);
         if (pos < 0 || pos >= row.n_avail) {  // out of range: the generic kernel reports -inf
-            if (lane == 0 && blockIdx.y == 0 && blockIdx.z == 0) vp.slow_flags[v] = 1u;
+            if (lane == 0 && blockIdx.y == 0 && blockIdx.z == 0 && atomicExch(&vp.slow_flags[v], 1u) == 0u)
+                vp.slow_list[atomicAdd(vp.slow_count, 1u)] = (unsigned)v;
             continue;
         }
         {
@@ -87,7 +95,8 @@ __global__ void __launch_bounds__(32) variant_regtab_kernel(const VariantParams 
             }
         }
         if (slow) {  // warp-uniform: leave this SNV to the generic kernel
-            if (lane == 0 && blockIdx.y == 0 && blockIdx.z == 0) vp.slow_flags[v] = 1u;
+            if (lane == 0 && blockIdx.y == 0 && blockIdx.z == 0 && atomicExch(&vp.slow_flags[v], 1u) == 0u)
+                vp.slow_list[atomicAdd(vp.slow_count, 1u)] = (unsigned)v;
             continue;
         }
         // per-lane range of steps whose completed window is valid: covers pos, starts >= 0, ends inside the sequence
@@ -127,9 +136,245 @@ __global__ void __launch_bounds__(32) variant_regtab_kernel(const VariantParams 
             res[pass] = mx;
         }
         if (motif >= 0) {
-            vp.ref_max[v * p.n_motifs + motif] = res[0];
-            vp.alt_max[v * p.n_motifs + motif] = res[1];
+            vp.ref_max[v * vp.snv_stride + motif * vp.motif_stride] = res[0];
+            vp.alt_max[v * vp.snv_stride + motif * vp.motif_stride] = res[1];
         }
+    }
+}
+
+// ---- triangular variant of the same kernel (padded widths up to kVariantTriMaxWB) ------------------------------------
+// The shift register above feeds 2*WB-1 bases through WB-1 partial sums twice (reference pass, alternate pass):
+// ~8*WB^2 additions per (SNV, PWM) against the 2*(WB^2 + WB) the problem needs, because half of the partial
+// windows it advances start before the first fed base or end after the last one and are thrown away, and because the
+// alternate pass repeats every term of the reference pass.  Here the 2*WB-1 steps are fully unrolled, so step i only
+// touches the windows that really contain fed base i (window j = fed bases j .. j+WB-1, a static register each), and the
+// alternate sums FORK from the reference sums at the SNV's own step: alt_j = prefix_j + T[k_j][alt], after which both
+// sums receive the same remaining terms.  Every sum is still the fixed ascending-k fp32 sum of the oracle (bit-identical
+// results), for WB^2 + WB*(WB-1)/2 + WB packed additions: 1.5x the algorithmic count instead of 4x.
+//
+// FORK = false is the cheaper formulation VERDICT r1 asked for: alt_j = (ref_j - T[k_j][ref]) + T[k_j][alt], 2*WB packed
+// operations after the WB^2 of the reference sums (the algorithmic count), half the window registers (one more resident
+// warp per scheduler) and a third less code.  Its alternate scores differ from the fresh ascending-k sum by a few ulp
+// of the largest partial sum (tests: |diff| <= 1e-5 * sum_k max_b |T[k][b]|), so it is only taken when every table
+// entry is finite (an infinite term would turn the subtraction into NaN); the reference maxima stay bit-identical.
+constexpr int kVariantTriMaxWB = 16;
+
+// fed base I (a compile-time step) = reference base B: advance every window that contains it
+#define SMG_TRI_STEP(I, B)                                                        \
+    {                                                                             \
+        _Pragma("unroll") for (int j = 0; j < WB; ++j) {                          \
+            const int k = (I) - j;                                                \
+            if (k == 0) a[j] = t.get(0, B);                                       \
+            else if (k > 0 && k < WB) {                                           \
+                a[j] = vadd(a[j], t.get(k, B));                                   \
+                if (FORK && (I) > WB - 1) b[j] = vadd(b[j], t.get(k, B));         \
+            }                                                                     \
+        }                                                                         \
+    }
+// delta formulation, after the last step: remove the reference base's term ... (k_j = WB-1-j is the SNV's offset in window j)
+#define SMG_TRI_SUB(B)                                                            \
+    {                                                                             \
+        _Pragma("unroll") for (int j = 0; j < WB; ++j)                            \
+            a[j] = __ffma2_rn(t.get(WB - 1 - j, B), make_float2(-1.f, -1.f), a[j]); \
+    }
+// ... and add the alternate base's
+#define SMG_TRI_ADD(B)                                                            \
+    {                                                                             \
+        _Pragma("unroll") for (int j = 0; j < WB; ++j) a[j] = vadd(a[j], t.get(WB - 1 - j, B)); \
+    }
+// the SNV's own step (fed index WB-1): the alternate sums take the alternate base's term on top of the shared prefix
+#define SMG_TRI_FORK(B)                                                           \
+    {                                                                             \
+        _Pragma("unroll") for (int j = 0; j < WB; ++j) {                          \
+            const int k = WB - 1 - j;                                             \
+            b[j] = k == 0 ? t.get(0, B) : vadd(a[j], t.get(k, B));                \
+        }                                                                         \
+    }
+
+__device__ __forceinline__ float vmax3(const float a, const float b, const float c)
+{
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+template <int WB, bool FORK>
+__global__ void __launch_bounds__(32, (!FORK && WB == 12) ? 20 : 1) variant_tri_kernel(const VariantParams vp)
+{
+    using V = float2;
+    static_assert(2 * WB - 1 <= 32, "the fed bases must fit one 64-bit word");
+    const ScanParams& p = vp.sp;
+    const int lane = threadIdx.x;
+    const int group = p.first_group + blockIdx.y;
+    const int sub = blockIdx.z;  // PWM slot of the lane group handled by this CTA
+    Tab<WB> t;
+    t.load(p.group_tab + p.group_tab_off[group] + (size_t)sub * (WB * 4 * 32 * 2), lane);
+    const int motif = p.lane_motif[(group * SMG_MAX_PWMS_PER_LANE + sub) * 32 + lane];
+    const int wm = motif >= 0 ? p.motif_width[motif] : 1;
+    const int rc_shift = WB - (motif >= 0 ? wm : WB);  // head-padded RC table: its window completes rc_shift steps earlier
+    // every real lane as wide as the padded width (the usual case: groups are formed by width) -> away from the row ends
+    // all WB windows of both strands are valid and the maxima need no per-window predicates
+    const bool full_width = __all_sync(SMG_FULL_MASK, motif < 0 || wm == WB);
+    const float ninf = __int_as_float(0xff800000);
+    constexpr int NSTEP = 2 * WB - 1;
+
+    // the bases around one SNV, fetched one SNV AHEAD of the arithmetic (the loads are dependent: position -> words)
+    struct Fed {
+        uint32_t w0, w1;  // fed base i = bits 2i, 2i+1 of (w1:w0)
+        long long pos, span;
+        int alt;
+        bool skip;  // warp-uniform: out of range or ambiguity codes nearby -> generic kernel
+    };
+    auto fetch = [&](const long long v) {
+        Fed f;
+        f.w0 = f.w1 = 0u;
+        f.pos = 0; f.span = 0; f.alt = 1; f.skip = true;
+        if (v >= vp.n_snv) return f;
+        const smg_row_t row = p.rows[vp.snv_row[v]];
+        f.pos = vp.snv_pos[v];
+        f.alt = vp.snv_alt[v];
+        f.span = row.g_len - row.g_off;
+        if (f.pos < 0 || f.pos >= row.n_avail) return f;
+        bool slow = (f.alt < 1 || f.alt > 5);
+        const long long q0 = f.pos - (WB - 1);
+        const long long qa = q0 < 0 ? 0 : q0;
+        const long long wfirst = row.word_off + (qa >> 4);
+        const uint32_t x0 = p.packed[wfirst], x1 = p.packed[wfirst + 1], x2 = p.packed[wfirst + 2];
+        const unsigned amb = (unsigned)p.amask[wfirst] | (unsigned)p.amask[wfirst + 1] | (unsigned)p.amask[wfirst + 2];
+        if (amb) {  // restrict the ambiguity test to the fed bases inside the row
+            const long long qend = q0 + NSTEP;
+            for (long long q = qa; q < qend && q < row.n_avail; ++q)
+                if ((p.amask[row.word_off + (q >> 4)] >> (q & 15)) & 1) slow = true;
+        }
+        const int sh = 2 * (int)(qa & 15);
+        unsigned long long lo = ((unsigned long long)x0 | ((unsigned long long)x1 << 32)) >> sh;
+        if (sh) lo |= (unsigned long long)x2 << (64 - sh);
+        lo <<= 2 * (int)(qa - q0);  // bases before the start of the sequence are fed as 'A' (their windows are invalid)
+        f.w0 = (uint32_t)lo; f.w1 = (uint32_t)(lo >> 32); f.skip = slow;
+        return f;
+    };
+
+    // Output.  With the SNV index as the fastest dimension (snv_stride == 1, "motif-major") the scores of a batch are
+    // staged in shared memory and written as whole 128-byte lines.  In the [n_snv][n_motifs] layout each warp writes 32
+    // scattered-width floats into a 4*n_motifs-byte row that other launches complete later: partial sectors, and the L2
+    // has to read every line back before it can write it (measured: 6.7 GB of DRAM traffic per launch for 0.77 GB).
+    const bool transposed = vp.snv_stride == 1;
+    __shared__ float stage[2][32][33];
+    // each lane fetches ONE SNV of a batch of 32 consecutive ones (the three dependent loads of all 32 overlap, and the
+    // next batch is requested before this one is scored); the warp then walks the batch, broadcasting by shuffle
+    const long long stride = (long long)gridDim.x * 32;
+    Fed mine = fetch((long long)blockIdx.x * 32 + lane);
+    for (long long v0 = (long long)blockIdx.x * 32; v0 < vp.n_snv; v0 += stride) {
+      const Fed got = mine;
+      mine = fetch(v0 + stride + lane);
+      const int cnt = (int)(vp.n_snv - v0 < 32 ? vp.n_snv - v0 : 32);
+      unsigned done_mask = 0u;  // SNVs of this batch scored here (the others are left to the generic kernel)
+#pragma unroll 1
+      for (int sl = 0; sl < cnt; ++sl) {
+        const long long v = v0 + sl;
+        Fed cur;
+        cur.w0 = __shfl_sync(SMG_FULL_MASK, got.w0, sl);
+        cur.w1 = __shfl_sync(SMG_FULL_MASK, got.w1, sl);
+        cur.pos = __shfl_sync(SMG_FULL_MASK, got.pos, sl);
+        cur.span = __shfl_sync(SMG_FULL_MASK, got.span, sl);
+        cur.alt = __shfl_sync(SMG_FULL_MASK, got.alt, sl);
+        cur.skip = __shfl_sync(SMG_FULL_MASK, (int)got.skip, sl) != 0;
+        if (cur.skip) {
+            if (lane == 0 && blockIdx.y == 0 && blockIdx.z == 0 && atomicExch(&vp.slow_flags[v], 1u) == 0u)
+                vp.slow_list[atomicAdd(vp.slow_count, 1u)] = (unsigned)v;
+            continue;
+        }
+        V a[WB], b[WB];
+#pragma unroll
+        for (int j = 0; j < WB; ++j) a[j] = b[j] = V{};
+        const int a2 = cur.alt == 5 ? 3 : cur.alt - 1;
+#pragma unroll
+        for (int i = 0; i < NSTEP; ++i) {
+            const uint32_t word = i < 16 ? cur.w0 : cur.w1;
+            const uint32_t hi_bit = 2u << (2 * (i & 15)), lo_bit = 1u << (2 * (i & 15));
+            if (FORK && i == WB - 1) {
+                if (a2 & 2) {
+                    if (a2 & 1) SMG_TRI_FORK(3) else SMG_TRI_FORK(2)
+                } else {
+                    if (a2 & 1) SMG_TRI_FORK(1) else SMG_TRI_FORK(0)
+                }
+            }
+            if (word & hi_bit) {
+                if (word & lo_bit) SMG_TRI_STEP(i, 3) else SMG_TRI_STEP(i, 2)
+            } else {
+                if (word & lo_bit) SMG_TRI_STEP(i, 1) else SMG_TRI_STEP(i, 0)
+            }
+        }
+        // maximum over the valid windows of both strands
+        const long long pos = cur.pos;
+        const bool interior = full_width && pos >= WB - 1 && pos <= cur.span - WB;
+        int lo_f = 0, hi_f = WB - 1, lo_r = 0, hi_r = WB - 1;
+        if (!interior) {  // per-lane range of windows that are valid: cover pos, start >= 0, end inside the sequence
+            const long long smax64 = cur.span - (long long)wm;
+            long long imin = 2 * (WB - 1) - wm + 1;
+            const long long need0 = 2 * (WB - 1) - pos;  // s_i >= 0
+            if (need0 > imin) imin = need0;
+            long long imax = smax64 - pos + 2 * (WB - 1);  // s_i <= smax
+            if (imax > 2 * (WB - 1)) imax = 2 * (WB - 1);
+            lo_f = (int)imin - (WB - 1); hi_f = (int)imax - (WB - 1);  // forward strand
+            lo_r = lo_f - rc_shift; hi_r = hi_f - rc_shift;            // reverse-complement strand
+        }
+        auto window_max = [&](const V(&x)[WB]) {
+            float mx = ninf;
+            if (interior) {
+#pragma unroll
+                for (int j = 0; j < WB; ++j) mx = vmax3(mx, x[j].x, x[j].y);
+            } else {
+#pragma unroll
+                for (int j = 0; j < WB; ++j) {
+                    if (j >= lo_f && j <= hi_f) mx = fmaxf(mx, x[j].x);
+                    if (j >= lo_r && j <= hi_r) mx = fmaxf(mx, x[j].y);
+                }
+            }
+            return mx;
+        };
+        const float rmx = window_max(a);
+        float amx;
+        if (FORK) {
+            amx = window_max(b);
+        } else {  // delta form, in place: a_j <- (a_j - T[k_j][ref]) + T[k_j][alt]
+            constexpr int ic = WB - 1;  // the SNV's fed index
+            const uint32_t word = ic < 16 ? cur.w0 : cur.w1;
+            const uint32_t hi_bit = 2u << (2 * (ic & 15)), lo_bit = 1u << (2 * (ic & 15));
+            if (word & hi_bit) {
+                if (word & lo_bit) SMG_TRI_SUB(3) else SMG_TRI_SUB(2)
+            } else {
+                if (word & lo_bit) SMG_TRI_SUB(1) else SMG_TRI_SUB(0)
+            }
+            if (a2 & 2) {
+                if (a2 & 1) SMG_TRI_ADD(3) else SMG_TRI_ADD(2)
+            } else {
+                if (a2 & 1) SMG_TRI_ADD(1) else SMG_TRI_ADD(0)
+            }
+            amx = window_max(a);
+        }
+        if (transposed) {  // stage; the batch is written below as full lines
+            stage[0][sl][lane] = rmx;
+            stage[1][sl][lane] = amx;
+            done_mask |= 1u << sl;
+        } else if (motif >= 0) {
+            vp.ref_max[v * vp.snv_stride + motif * vp.motif_stride] = rmx;
+            vp.alt_max[v * vp.snv_stride + motif * vp.motif_stride] = amx;
+        }
+      }
+      if (transposed) {  // motif-major output: lane = SNV of the batch, one 128-byte line per (PWM, ref / alt)
+        __syncwarp();
+        const bool mine_ok = (done_mask >> lane) & 1u;
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            const int mr = __shfl_sync(SMG_FULL_MASK, motif, r);
+            if (mr >= 0 && mine_ok) {
+                vp.ref_max[(long long)mr * vp.motif_stride + v0 + lane] = stage[0][lane][r];
+                vp.alt_max[(long long)mr * vp.motif_stride + v0 + lane] = stage[1][lane][r];
+            }
+        }
+        __syncwarp();
+      }
     }
 }
 
@@ -137,7 +382,12 @@ template <int WB>
 void launch_variant_regtab(const VariantParams& vp, int n_blocks, int n_groups, int nm, cudaStream_t stream)
 {
     dim3 grid((unsigned)n_blocks, (unsigned)n_groups, (unsigned)nm);
-    variant_regtab_kernel<WB><<<grid, 32, 0, stream>>>(vp);
+    if constexpr (WB <= kVariantTriMaxWB) {
+        if (vp.exact) variant_tri_kernel<WB, true><<<grid, 32, 0, stream>>>(vp);
+        else variant_tri_kernel<WB, false><<<grid, 32, 0, stream>>>(vp);
+    } else {
+        variant_regtab_kernel<WB><<<grid, 32, 0, stream>>>(vp);
+    }
 }
 
 }  // namespace smg

@@ -114,31 +114,43 @@ def variant_effect_on_sites(sites, variants, seqs, pwms):
     return res
 
 
-def variant_window_scores(seqs, snv_row, snv_pos, snv_alt, pwms, to_host=True):
+def variant_window_scores(seqs, snv_row, snv_pos, snv_alt, pwms, to_host=True, exact=False):
     """Batched SNV scoring (BASELINE config 5): for every SNV (row index into seqs, 0-based position, alternate base)
     and every PWM, the maximum reference and alternate score over all windows covering the SNV on both strands.
-    Returns (ref_max, alt_max) float32 arrays of shape (n_snv, n_motifs); delta = alt_max - ref_max."""
+    Returns (ref_max, alt_max) float32 arrays of shape (n_snv, n_motifs); delta = alt_max - ref_max.
+
+    exact=False (default): alternate window scores are formed as (reference score - T[k, ref]) + T[k, alt], which is
+    what makes the batch cheap; they agree with a fresh fp32 sum to a few ulp of the largest partial sum.  exact=True
+    forks the alternate sums from the reference sums instead (bit-identical to the fresh ascending-k sum, ~1.3x slower).
+    Reference maxima are bit-identical either way."""
     model = _model_for(pwms)
     strings = [seq_str(r) if not isinstance(r, (bytes, np.ndarray)) else r for r in seqs]
     batch = dev.SeqBatch(strings, kind="ascii")
-    return variant_window_scores_on_batch(batch, snv_row, snv_pos, snv_alt, model, to_host)
+    return variant_window_scores_on_batch(batch, snv_row, snv_pos, snv_alt, model, to_host, exact)
 
 
-def variant_window_scores_on_batch(batch, snv_row, snv_pos, snv_alt, model, to_host=True):
+def variant_window_scores_on_batch(batch, snv_row, snv_pos, snv_alt, model, to_host=True, exact=False, motif_major=True):
     dset = model.device_set
     d = batch.device
     n = len(snv_pos)
-    if isinstance(snv_alt, np.ndarray) and snv_alt.dtype == np.uint8:
+    if isinstance(snv_alt, torch.Tensor) or (isinstance(snv_alt, np.ndarray) and snv_alt.dtype == np.uint8):
         alt = snv_alt
     else:
         alt = np.array([integer_encoding_dict[a] for a in snv_alt], dtype=np.uint8)
-    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(d)  # noqa: E731
-    ref_max = torch.empty((n, dset.n_motifs), dtype=torch.float32, device=d)
-    alt_max = torch.empty((n, dset.n_motifs), dtype=torch.float32, device=d)
+    def t(a, dt):  # device tensors are taken as they are (a resident batch of SNVs scored repeatedly)
+        if isinstance(a, torch.Tensor):
+            return a.to(device=d, dtype={np.int32: torch.int32, np.uint8: torch.uint8}[dt]).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(d)
+    # motif-major storage (the layout the kernels can write as whole lines), handed back as (n_snv, n_motifs) views
+    shape = (dset.n_motifs, n) if motif_major else (n, dset.n_motifs)
+    ref_max = torch.empty(shape, dtype=torch.float32, device=d)
+    alt_max = torch.empty(shape, dtype=torch.float32, device=d)
     a_row, a_pos, a_alt = t(snv_row, np.int32), t(snv_pos, np.int32), t(alt, np.uint8)
-    _lib.check(_lib.load().smg_variant_windows(dset.handle, dev._ptr(batch.packed), dev._ptr(batch.amask), dev._ptr(batch.codes),
-                                               dev._ptr(batch.d_rows), dev._ptr(a_row), dev._ptr(a_pos), dev._ptr(a_alt), n,
-                                               dev._ptr(ref_max), dev._ptr(alt_max), dev._stream()), "smg_variant_windows")
+    _lib.check(_lib.load().smg_variant_windows_mode(dset.handle, dev._ptr(batch.packed), dev._ptr(batch.amask),
+                                                    dev._ptr(batch.codes), dev._ptr(batch.d_rows), dev._ptr(a_row),
+                                                    dev._ptr(a_pos), dev._ptr(a_alt), n, dev._ptr(ref_max), dev._ptr(alt_max),
+                                                    1 if exact else 0, 1 if motif_major else 0, dev._stream()),
+               "smg_variant_windows_mode")
     if to_host:
-        return ref_max.cpu().numpy(), alt_max.cpu().numpy()
-    return ref_max, alt_max
+        ref_max, alt_max = ref_max.cpu().numpy(), alt_max.cpu().numpy()
+    return (ref_max.T, alt_max.T) if motif_major else (ref_max, alt_max)

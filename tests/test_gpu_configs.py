@@ -224,10 +224,13 @@ def test_c3_shuffled_backgrounds_counts_and_stats():
     np.testing.assert_allclose(got_s["sd"], exp_stats["sd"], rtol=1e-9)
 
 
-def test_c5_variant_windows_10k_snvs_vs_c_oracle():
+@pytest.mark.parametrize("exact", [False, True])
+def test_c5_variant_windows_10k_snvs_vs_c_oracle(exact):
     """Config c5 shape: 10,000 SNVs from the c5 generator (synth.snvs) on a 200 kb reference x 500 PWMs (W 7-12):
-    maximum reference / alternate window score over the covering windows of both strands, against the C oracle
-    (same fp32 summation order: bit-identical is expected, 1e-5 relative is the bar)."""
+    maximum reference / alternate window score over the covering windows of both strands, against the C oracle.
+    Reference maxima: same fp32 summation order, bit-identical.  Alternate maxima: bit-identical in the exact (forked
+    sums) mode; in the default delta mode (ref - T[k, ref] + T[k, alt]) within 1e-5 of the PWM's score scale
+    sum_k max_b |T[k, b]| -- the tolerance north_star states for floating-point scores."""
     import smeagol_b200 as sb
     from oracle import c_oracle
     from smeagol_b200 import device as dev
@@ -238,13 +241,22 @@ def test_c5_variant_windows_10k_snvs_vs_c_oracle():
     pos, alt = synth.snvs(seq, 10_000, 12, seed=5)
     model = sb.models.PWMModel(pw)
     batch = dev.SeqBatch([seq])
-    ref_max, alt_max = variant.variant_window_scores_on_batch(batch, np.zeros(len(pos), dtype=np.int32), pos, alt, model)
+    ref_max, alt_max = variant.variant_window_scores_on_batch(batch, np.zeros(len(pos), dtype=np.int32), pos, alt, model,
+                                                              exact=exact)
     e_ref, e_alt = c_oracle.variant_windows(_LUT[seq], list(pw.weights), pos, alt)
-    np.testing.assert_allclose(ref_max, e_ref, rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(alt_max, e_alt, rtol=1e-5, atol=1e-6)
-    assert np.mean(ref_max.view(np.uint32) == e_ref.view(np.uint32)) > 0.999
+    assert np.array_equal(ref_max, e_ref)
+    if exact:
+        assert np.array_equal(alt_max, e_alt)
+    else:
+        scale = np.array([np.abs(np.asarray(w)).max(axis=1).sum() for w in pw.weights], dtype=np.float64)
+        assert np.all(np.abs(alt_max.astype(np.float64) - e_alt) <= 1e-5 * scale[None, :])
+        assert np.mean(alt_max == e_alt) > 0.2  # many windows still round the same way
     # the delta the config reports: an SNV changes at least one PWM's best window for nearly every SNV
     assert np.mean(np.any(alt_max != ref_max, axis=1)) > 0.99
+    # the [n_snv][n_motifs] layout of the C ABI holds the same numbers
+    r2, a2 = variant.variant_window_scores_on_batch(batch, np.zeros(len(pos), dtype=np.int32), pos, alt, model, exact=exact,
+                                                    motif_major=False)
+    assert r2.shape == ref_max.shape and np.array_equal(r2, ref_max) and np.array_equal(a2, alt_max)
 
 
 def test_shuffle_fixture_of_the_reference():
