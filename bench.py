@@ -291,6 +291,7 @@ def run_c4(args, rank, world, local_rank, device, peaks, peaks_kind, warmup):
         plan.counters.zero_()
         plan.counts.zero_()
         if plan.engine == "auto":
+            plan.launch_kmer_build()  # per-call index of (PWM set, thresholds): inside the step
             plan.launch_kmer_side()
             if ev:
                 ev[5].record()
@@ -463,6 +464,7 @@ def run_c2(args, rank, world, local_rank, device, peaks, peaks_kind, warmup, ste
         plan.counters.zero_()
         plan.counts.zero_()
         if plan.engine == "auto":
+            plan.launch_kmer_build()  # per-call index of (PWM set, thresholds): inside the step
             plan.launch_kmer_side()
             plan.launch_regtab_side()
             if ev:

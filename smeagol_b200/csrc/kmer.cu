@@ -9,8 +9,9 @@
 //
 //   index   head[class offset + x]        first entry of k-mer x (or -1); x = sum_k base(p + k) << 2k
 //           entry {col | flags, score, next}   col = motif * 2 + strand; singly linked (built in one pass with atomicExch)
-//   build   one thread = one (W-2)-base prefix x one column tile: the prefix sum is shared by the 16 k-mers that extend it
-//           (same rounding as a sequential sum, since the order is ascending k)
+//   build   one thread = one (W-3)-base prefix x one column tile: the prefix sum is shared by the 64 k-mers that extend it
+//           (same rounding as a sequential sum, since the order is ascending k), and an exact upper bound of the
+//           extensions prunes almost every prefix before any of them is formed (branch and bound)
 //   scan    one thread = one window start; a CTA stages its hits in shared memory and appends them to the global hit list
 //           with one atomic per flush; per-(motif, strand) counts in a shared-memory histogram, flushed per chunk
 //   windows that contain an IUPAC code, 'Z' or the end of the row are scored directly (rare generic path).
@@ -24,7 +25,48 @@
 namespace smg {
 
 // ---------------------------------------------------------------------------------------------------- build
-// grid.x: prefixes of (W - tail) bases, 128 per CTA; grid.y: tiles of 16 motifs of the class
+// grid.x: prefixes of (W - TAIL) bases, 128 per CTA; grid.y: tiles of 16 motifs of the class.
+//
+// BRANCH AND BOUND: rounded fp32 addition is monotone in each operand, so the score of every k-mer that extends a
+// prefix is bounded by the SAME chain of additions fed with the per-position maxima,
+//     ub = ((acc + max_b T[W-3][b]) + max_b T[W-2][b]) + max_b T[W-1][b]      (fixed order, fp32, every step rounded)
+// -- an exact bound, not an estimate.  At hit densities of 1e-4 .. 6e-3 almost every prefix fails `ub > thr_lo` and its
+// 64 extensions are never formed; the survivors are expanded by the whole warp (lane = extension).
+__device__ __forceinline__ void kmer_emit_entry(const KmerParams& kp, const ScanParams& p, const int W, const long long x,
+                                                const float s, const float* tab, const int st, const int last, const int motif,
+                                                const float hi, const double t64, int32_t* head)
+{
+    uint32_t flags = 0;
+    if (!(s > hi)) {  // near-threshold band: decide in fp64 (same operands, same order)
+        double a64 = 0.0;
+        for (int k = 0; k < W; ++k) {
+            const int j = 4 * k + (int)((x >> (2 * k)) & 3);
+            const double term = (double)tab[st ? (last - j) : j];
+            a64 = (k == 0) ? term : __dadd_rn(a64, term);
+        }
+        flags = kEntNear | ((a64 > t64) ? 0u : kEntRej);
+    }
+    const unsigned long long idx = atomicAdd(&p.counters[SMG_CTR_KMER_ENTRIES], 1ull);
+    if (idx < kp.entry_cap) {
+        smg_kmer_entry_t e;
+        e.col = (uint32_t)(motif * 2 + st) | flags;
+        e.score = s;
+        e.next = atomicExch(&head[x], (int32_t)idx);
+        atomicOr(reinterpret_cast<unsigned*>(kp.head + kp.bm_off[W]) + (x >> 5), 1u << (x & 31));
+        if (W >= kKmerBitmapMinW && kp.max_w > kKmerBitmapMinW) {
+            // combined bitmap of the wide classes, keyed by the max_w-mer: every extension of this k-mer
+            unsigned* cb = reinterpret_cast<unsigned*>(kp.head + kp.cb_off);
+            const long long n_ext = 1ll << (2 * (kp.max_w - W));
+            for (long long t2 = 0; t2 < n_ext; ++t2) {
+                const long long y = x | (t2 << (2 * W));
+                atomicOr(cb + (y >> 5), 1u << (y & 31));
+            }
+        }
+        e.reserved = 0;
+        kp.entries[idx] = e;
+    }
+}
+
 template <int TAIL>
 __global__ void __launch_bounds__(128) kmer_build_kernel(const KmerParams kp, const int W)
 {
@@ -53,60 +95,61 @@ __global__ void __launch_bounds__(128) kmer_build_kernel(const KmerParams kp, co
     const int pre = W - TAIL;
     const long long n_pre = 1ll << (2 * pre);
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n_pre) return;
+    const bool active = q < n_pre;  // (whole warps stay: the expansion below is warp-cooperative)
+    const int lane = threadIdx.x & 31;
     const int last = 4 * W - 1;
+    constexpr int kExt = 1 << (2 * TAIL);  // extensions of one prefix
+    int off[kKmerMaxW - TAIL];             // table offsets of this thread's prefix bases (the same for every column)
+#pragma unroll
+    for (int k = 0; k < kKmerMaxW - TAIL; ++k) off[k] = 4 * k + (int)((q >> (2 * k)) & 3);
     int32_t* head = kp.head + kp.head_off[W];
     for (int t = 0; t < nt; ++t) {
         const float* tab = s_tab[t];
+        const float lo = s_lo[t];
         for (int st = 0; st < 2; ++st) {
             if (!((p.strands >> st) & 1)) continue;
             // forward: T[k][b] = tab[4k + b]; reverse complement on the forward string: tab[last - (4k + b)]
-            float acc = 0.f;
-            for (int k = 0; k < pre; ++k) {
-                const int j = 4 * k + (int)((q >> (2 * k)) & 3);
-                const float term = tab[st ? (last - j) : j];
-                acc = (k == 0) ? term : __fadd_rn(acc, term);
+            float mx[TAIL];
+#pragma unroll
+            for (int u = 0; u < TAIL; ++u) {
+                const int j = 4 * (pre + u);
+                const float4 v = st ? make_float4(tab[last - j], tab[last - j - 1], tab[last - j - 2], tab[last - j - 3])
+                                    : make_float4(tab[j], tab[j + 1], tab[j + 2], tab[j + 3]);
+                mx[u] = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
             }
+            float acc = 0.f;
 #pragma unroll
-            for (int tl = 0; tl < (1 << (2 * TAIL)); ++tl) {
-                float s = acc;
+            for (int k = 0; k < kKmerMaxW - TAIL; ++k) {
+                if (k < pre) {
+                    const float term = tab[st ? (last - off[k]) : off[k]];
+                    acc = (k == 0) ? term : __fadd_rn(acc, term);
+                }
+            }
+            // exact upper bound of all 4^TAIL extensions (same chain of rounded additions, maxima as operands)
+            float ub = (pre == 0) ? mx[0] : __fadd_rn(acc, mx[0]);
 #pragma unroll
-                for (int u = 0; u < TAIL; ++u) {
-                    const int k = pre + u;
-                    const int j = 4 * k + ((tl >> (2 * u)) & 3);
-                    const float term = tab[st ? (last - j) : j];
-                    s = (k == 0) ? term : __fadd_rn(s, term);
-                }
-                if (!(s > s_lo[t])) continue;
-                const long long x = q | ((long long)tl << (2 * pre));
-                uint32_t flags = 0;
-                if (!(s > s_hi[t])) {  // near-threshold band: decide in fp64 (same operands, same order)
-                    double a64 = 0.0;
-                    for (int k = 0; k < W; ++k) {
-                        const int j = 4 * k + (int)((x >> (2 * k)) & 3);
-                        const double term = (double)tab[st ? (last - j) : j];
-                        a64 = (k == 0) ? term : __dadd_rn(a64, term);
+            for (int u = 1; u < TAIL; ++u) ub = __fadd_rn(ub, mx[u]);
+            unsigned surv = __ballot_sync(SMG_FULL_MASK, active && ub > lo);
+            if (!surv) continue;
+            const float hi = s_hi[t];
+            const double t64 = s_t64[t];
+            const int motif = s_m[t];
+            // the surviving prefixes are expanded by the WHOLE warp, one prefix at a time (lane = extension): a lane
+            // walking its own 64 extensions would hold the other 31 idle through ~300 instructions
+            while (surv) {
+                const int src = __ffs(surv) - 1;
+                surv &= surv - 1;
+                const float a = __shfl_sync(SMG_FULL_MASK, acc, src);
+                const long long qs = __shfl_sync(SMG_FULL_MASK, q, src);
+                for (int e = lane; e < kExt; e += 32) {
+                    float sc = a;
+#pragma unroll
+                    for (int u = 0; u < TAIL; ++u) {
+                        const int j = 4 * (pre + u) + ((e >> (2 * u)) & 3);
+                        const float term = tab[st ? (last - j) : j];
+                        sc = (pre + u == 0) ? term : __fadd_rn(sc, term);
                     }
-                    flags = kEntNear | ((a64 > s_t64[t]) ? 0u : kEntRej);
-                }
-                const unsigned long long idx = atomicAdd(&p.counters[SMG_CTR_KMER_ENTRIES], 1ull);
-                if (idx < kp.entry_cap) {
-                    smg_kmer_entry_t e;
-                    e.col = (uint32_t)(s_m[t] * 2 + st) | flags;
-                    e.score = s;
-                    e.next = atomicExch(&head[x], (int32_t)idx);
-                    atomicOr(reinterpret_cast<unsigned*>(kp.head + kp.bm_off[W]) + (x >> 5), 1u << (x & 31));
-                    if (W >= kKmerBitmapMinW && kp.max_w > kKmerBitmapMinW) {
-                        // combined bitmap of the wide classes, keyed by the max_w-mer: every extension of this k-mer
-                        unsigned* cb = reinterpret_cast<unsigned*>(kp.head + kp.cb_off);
-                        const long long n_ext = 1ll << (2 * (kp.max_w - W));
-                        for (long long t2 = 0; t2 < n_ext; ++t2) {
-                            const long long y = x | (t2 << (2 * W));
-                            atomicOr(cb + (y >> 5), 1u << (y & 31));
-                        }
-                    }
-                    e.reserved = 0;
-                    kp.entries[idx] = e;
+                    if (sc > lo) kmer_emit_entry(kp, p, W, qs | ((long long)e << (2 * pre)), sc, tab, st, last, motif, hi, t64, head);
                 }
             }
         }
@@ -431,10 +474,11 @@ cudaError_t smg_kmer_launch_build(const smg::KmerParams& kp, cudaStream_t st, ui
     for (int W = 1; W <= kp.max_w; ++W) {
         const int n_cm = kp.cls_off[W + 1] - kp.cls_off[W];
         if (n_cm == 0) continue;
-        const int tail = std::min(W, 2);
+        const int tail = std::min(W, 3);
         const long long n_pre = 1ll << (2 * (W - tail));
         dim3 grid((unsigned)((n_pre + 127) / 128), (unsigned)((n_cm + 15) / 16), 1);
-        if (tail == 2) smg::kmer_build_kernel<2><<<grid, 128, 0, st>>>(kp, W);
+        if (tail == 3) smg::kmer_build_kernel<3><<<grid, 128, 0, st>>>(kp, W);
+        else if (tail == 2) smg::kmer_build_kernel<2><<<grid, 128, 0, st>>>(kp, W);
         else smg::kmer_build_kernel<1><<<grid, 128, 0, st>>>(kp, W);
         ++*n_launches;
         cudaError_t e = cudaGetLastError();

@@ -21,7 +21,7 @@ STRANDS = {"none": 1, "only": 2, "both": 3}
 DEFAULT_ENGINE = "regtab"
 DEFAULT_TC_KIND = "tc5"
 KMER_MAX_WIDTH = 12   # widest class of the k-mer index engine (csrc/kmer.cu)
-KMER_ALPHA = 1.0      # a width class W joins the k-mer index when 4^W <= KMER_ALPHA * (window starts of the scan): scoring all
+KMER_ALPHA = 1.5     # a width class joins the k-mer index when 4^W <= KMER_ALPHA * window starts (break-even of index build vs tcgen05 scan, profiles/r02_bench_widths.txt)
                       # k-mers once costs about as much per (k-mer, PWM) as any engine spends per (position, PWM)  # tensor-core prefilter of the 'auto' / tensor-core engines: 'hmma' (mma.sync) or 'tc5' (tcgen05 + TMEM)
 DEFAULT_TC_MIN_WIDTH = 7  # measured per width (profiles/r01_bench_widths.txt): the register-table engine wins up to W = 6 (hit density >= 6e-3 at thr 0.7), the tensor-core prefilter from W = 7
 
@@ -398,6 +398,17 @@ class ScanPlan:
                 raise _lib.SmeagolB200Error("k-mer index too large (threshold too low for the k-mer engine)")
             cap = min(int(need * 1.1) + 1024, (1 << 31) - 2)
         self.kmer_cap, self.kmer_n_entries = cap, need
+        self._kmer_hl, self._kmer_ctr = int(hl.value), ctr
+
+    def launch_kmer_build(self):
+        """Enqueue the k-mer index build again (same thresholds, known capacity, no host sync): what a fresh call pays
+        per (PWM set, thresholds) -- benchmarks put it inside the timed step."""
+        if self.kmer_w <= 0:
+            return
+        self._kmer_ctr.zero_()
+        _lib.check(self.lib.smg_kmer_index_build(self.pwmset.handle, self.kmer_w, self.strands, _ptr(self.d_lo), _ptr(self.d_hi),
+                                                 _ptr(self.d_thr), _ptr(self.kmer_head), self._kmer_hl, _ptr(self.kmer_entries),
+                                                 self.kmer_cap, _ptr(self._kmer_ctr), _stream()), "smg_kmer_index_build")
 
     def launch_kmer_side(self):
         """K-mer index engine on the width classes up to kmer_w (hits, counts and tallies like the other engines)."""
