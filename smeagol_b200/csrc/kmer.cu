@@ -9,9 +9,9 @@
 //
 //   index   head[class offset + x]        first entry of k-mer x (or -1); x = sum_k base(p + k) << 2k
 //           entry {col | flags, score, next}   col = motif * 2 + strand; singly linked (built in one pass with atomicExch)
-//   build   one thread = one (W-3)-base prefix x one column tile: the prefix sum is shared by the 64 k-mers that extend it
-//           (same rounding as a sequential sum, since the order is ascending k), and an exact upper bound of the
-//           extensions prunes almost every prefix before any of them is formed (branch and bound)
+//   build   one warp = one subtree of (W-3)-base prefixes x 16 motifs x 2 strands (lane = column), walked depth first: a
+//           prefix sum is one rounded addition on top of its parent's (same rounding as a sequential ascending-k sum),
+//           and an exact upper bound of the 64 extensions prunes almost every prefix before any of them is formed
 //   scan    one thread = one window start; a CTA stages its hits in shared memory and appends them to the global hit list
 //           with one atomic per flush; per-(motif, strand) counts in a shared-memory histogram, flushed per chunk
 //   windows that contain an IUPAC code, 'Z' or the end of the row are scored directly (rare generic path).
@@ -67,93 +67,130 @@ __device__ __forceinline__ void kmer_emit_entry(const KmerParams& kp, const Scan
     }
 }
 
+// One WARP = one subtree of prefixes x one tile of 16 motifs; lane = (motif of the tile, strand).  The prefix tree
+// (bases k = 0 .. pre-1, the ascending-k order of the sums) is walked depth first, so a node costs every lane ONE rounded
+// addition for its own column -- a prefix sum is never recomputed from k = 0 -- and a leaf costs the bound chain.
+constexpr int kBuildTile = 16;
+constexpr int kBuildRow = kKmerMaxW * 4 + 1;  // padded: the 16 rows of a tile start in 16 different banks
+
+struct KmerBuildCtx {
+    const KmerParams* kp;
+    const float* tab;      // this lane's column (shared memory)
+    const float* tab_all;  // the tile's tables
+    const float* s_hi;
+    const double* s_t64;
+    const int* s_m;
+    int32_t* head;
+    float lo, mx0, mx1, mx2;
+    int W, pre, d0, last, st, lane;
+    bool on;
+};
+
 template <int TAIL>
+__device__ __forceinline__ void kmer_build_leaf(const KmerBuildCtx& c, const float acc, const long long q)
+{
+    // exact upper bound of all 4^TAIL extensions (same chain of rounded additions, maxima as operands)
+    float ub = (c.pre == 0) ? c.mx0 : __fadd_rn(acc, c.mx0);
+    if (TAIL >= 2) ub = __fadd_rn(ub, c.mx1);
+    if (TAIL >= 3) ub = __fadd_rn(ub, c.mx2);
+    unsigned surv = __ballot_sync(SMG_FULL_MASK, c.on && ub > c.lo);
+    // surviving (prefix, column) pairs are expanded by the WHOLE warp, one at a time (lane = extension)
+    constexpr int kExt = 1 << (2 * TAIL);
+    while (surv) {
+        const int src = __ffs(surv) - 1;
+        surv &= surv - 1;
+        const float a = __shfl_sync(SMG_FULL_MASK, acc, src);
+        const float lo = __shfl_sync(SMG_FULL_MASK, c.lo, src);
+        const int t = src >> 1, st = src & 1;
+        const float* tab = c.tab_all + t * kBuildRow;
+        for (int e = c.lane; e < kExt; e += 32) {
+            float sc = a;
+#pragma unroll
+            for (int u = 0; u < TAIL; ++u) {
+                const int j = 4 * (c.pre + u) + ((e >> (2 * u)) & 3);
+                const float term = tab[st ? (c.last - j) : j];
+                sc = (c.pre + u == 0) ? term : __fadd_rn(sc, term);
+            }
+            if (sc > lo)
+                kmer_emit_entry(*c.kp, c.kp->sp, c.W, q | ((long long)e << (2 * c.pre)), sc, tab, st, c.last, c.s_m[t], c.s_hi[t],
+                                c.s_t64[t], c.head);
+        }
+    }
+}
+
+template <int DEPTH, int SUB, int TAIL> struct KmerBuildDfs {
+    static __device__ __forceinline__ void run(const KmerBuildCtx& c, const float acc, const long long q)
+    {
+        const int k = c.d0 + DEPTH;
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {
+            const int j = 4 * k + b;
+            const float term = c.tab[c.st ? (c.last - j) : j];
+            KmerBuildDfs<DEPTH + 1, SUB, TAIL>::run(c, k == 0 ? term : __fadd_rn(acc, term), q | ((long long)b << (2 * k)));
+        }
+    }
+};
+template <int SUB, int TAIL> struct KmerBuildDfs<SUB, SUB, TAIL> {
+    static __device__ __forceinline__ void run(const KmerBuildCtx& c, const float acc, const long long q)
+    {
+        kmer_build_leaf<TAIL>(c, acc, q);
+    }
+};
+
+// grid.x: subtrees (the first d0 = pre - SUB prefix bases), 4 per CTA; grid.y: tiles of 16 motifs of the class
+template <int SUB, int TAIL>
 __global__ void __launch_bounds__(128) kmer_build_kernel(const KmerParams kp, const int W)
 {
     const ScanParams& p = kp.sp;
-    constexpr int kTile = 16;
-    __shared__ float s_tab[kTile][kKmerMaxW * 4];
-    __shared__ float s_lo[kTile], s_hi[kTile];
-    __shared__ double s_t64[kTile];
-    __shared__ int s_m[kTile];
+    __shared__ float s_tab[kBuildTile * kBuildRow];
+    __shared__ float s_hi[kBuildTile];
+    __shared__ double s_t64[kBuildTile];
+    __shared__ int s_m[kBuildTile];
     const int c0 = kp.cls_off[W], n_cm = kp.cls_off[W + 1] - c0;
-    const int m0 = blockIdx.y * kTile;
-    const int nt = min(kTile, n_cm - m0);
+    const int m0 = blockIdx.y * kBuildTile;
+    const int nt = min(kBuildTile, n_cm - m0);
     for (int i = threadIdx.x; i < nt * W * 4; i += blockDim.x) {
         const int t = i / (W * 4), j = i % (W * 4);
         const int m = kp.cls_motifs[c0 + m0 + t];
-        s_tab[t][j] = p.nat_tab[p.motif_off[m] * 4 + j];
+        s_tab[t * kBuildRow + j] = p.nat_tab[p.motif_off[m] * 4 + j];
     }
     if (threadIdx.x < nt) {
         const int m = kp.cls_motifs[c0 + m0 + threadIdx.x];
         s_m[threadIdx.x] = m;
-        s_lo[threadIdx.x] = p.thr_lo[m];
         s_hi[threadIdx.x] = p.thr_hi[m];
         s_t64[threadIdx.x] = kp.thr64[m];
     }
     __syncthreads();
-    const int pre = W - TAIL;
-    const long long n_pre = 1ll << (2 * pre);
-    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = q < n_pre;  // (whole warps stay: the expansion below is warp-cooperative)
-    const int lane = threadIdx.x & 31;
-    const int last = 4 * W - 1;
-    constexpr int kExt = 1 << (2 * TAIL);  // extensions of one prefix
-    int off[kKmerMaxW - TAIL];             // table offsets of this thread's prefix bases (the same for every column)
+    KmerBuildCtx c;
+    c.kp = &kp;
+    c.W = W; c.pre = W - TAIL; c.d0 = c.pre - SUB; c.last = 4 * W - 1;
+    c.lane = threadIdx.x & 31;
+    const int t = c.lane >> 1;
+    c.st = c.lane & 1;
+    c.on = t < nt && ((p.strands >> c.st) & 1);
+    c.tab_all = s_tab; c.tab = s_tab + (t < nt ? t : 0) * kBuildRow;
+    c.s_hi = s_hi; c.s_t64 = s_t64; c.s_m = s_m;
+    c.head = kp.head + kp.head_off[W];
+    c.lo = c.on ? p.thr_lo[s_m[t]] : 0.f;
+    float mx[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int k = 0; k < kKmerMaxW - TAIL; ++k) off[k] = 4 * k + (int)((q >> (2 * k)) & 3);
-    int32_t* head = kp.head + kp.head_off[W];
-    for (int t = 0; t < nt; ++t) {
-        const float* tab = s_tab[t];
-        const float lo = s_lo[t];
-        for (int st = 0; st < 2; ++st) {
-            if (!((p.strands >> st) & 1)) continue;
-            // forward: T[k][b] = tab[4k + b]; reverse complement on the forward string: tab[last - (4k + b)]
-            float mx[TAIL];
-#pragma unroll
-            for (int u = 0; u < TAIL; ++u) {
-                const int j = 4 * (pre + u);
-                const float4 v = st ? make_float4(tab[last - j], tab[last - j - 1], tab[last - j - 2], tab[last - j - 3])
-                                    : make_float4(tab[j], tab[j + 1], tab[j + 2], tab[j + 3]);
-                mx[u] = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-            }
-            float acc = 0.f;
-#pragma unroll
-            for (int k = 0; k < kKmerMaxW - TAIL; ++k) {
-                if (k < pre) {
-                    const float term = tab[st ? (last - off[k]) : off[k]];
-                    acc = (k == 0) ? term : __fadd_rn(acc, term);
-                }
-            }
-            // exact upper bound of all 4^TAIL extensions (same chain of rounded additions, maxima as operands)
-            float ub = (pre == 0) ? mx[0] : __fadd_rn(acc, mx[0]);
-#pragma unroll
-            for (int u = 1; u < TAIL; ++u) ub = __fadd_rn(ub, mx[u]);
-            unsigned surv = __ballot_sync(SMG_FULL_MASK, active && ub > lo);
-            if (!surv) continue;
-            const float hi = s_hi[t];
-            const double t64 = s_t64[t];
-            const int motif = s_m[t];
-            // the surviving prefixes are expanded by the WHOLE warp, one prefix at a time (lane = extension): a lane
-            // walking its own 64 extensions would hold the other 31 idle through ~300 instructions
-            while (surv) {
-                const int src = __ffs(surv) - 1;
-                surv &= surv - 1;
-                const float a = __shfl_sync(SMG_FULL_MASK, acc, src);
-                const long long qs = __shfl_sync(SMG_FULL_MASK, q, src);
-                for (int e = lane; e < kExt; e += 32) {
-                    float sc = a;
-#pragma unroll
-                    for (int u = 0; u < TAIL; ++u) {
-                        const int j = 4 * (pre + u) + ((e >> (2 * u)) & 3);
-                        const float term = tab[st ? (last - j) : j];
-                        sc = (pre + u == 0) ? term : __fadd_rn(sc, term);
-                    }
-                    if (sc > lo) kmer_emit_entry(kp, p, W, qs | ((long long)e << (2 * pre)), sc, tab, st, last, motif, hi, t64, head);
-                }
-            }
-        }
+    for (int u = 0; u < TAIL; ++u) {  // forward: T[k][b] = tab[4k + b]; reverse complement: tab[last - (4k + b)]
+        const int j = 4 * (c.pre + u);
+        const float4 v = c.st ? make_float4(c.tab[c.last - j], c.tab[c.last - j - 1], c.tab[c.last - j - 2], c.tab[c.last - j - 3])
+                              : make_float4(c.tab[j], c.tab[j + 1], c.tab[j + 2], c.tab[j + 3]);
+        mx[u] = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
     }
+    c.mx0 = mx[0]; c.mx1 = mx[1]; c.mx2 = mx[2];
+    const long long n_sub = 1ll << (2 * c.d0);
+    const long long sub = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (sub >= n_sub) return;  // whole warps
+    float acc = 0.f;
+    for (int k = 0; k < c.d0; ++k) {
+        const int j = 4 * k + (int)((sub >> (2 * k)) & 3);
+        const float term = c.tab[c.st ? (c.last - j) : j];
+        acc = (k == 0) ? term : __fadd_rn(acc, term);
+    }
+    KmerBuildDfs<0, SUB, TAIL>::run(c, acc, sub);
 }
 
 // ---------------------------------------------------------------------------------------------------- scan
@@ -475,11 +512,20 @@ cudaError_t smg_kmer_launch_build(const smg::KmerParams& kp, cudaStream_t st, ui
         const int n_cm = kp.cls_off[W + 1] - kp.cls_off[W];
         if (n_cm == 0) continue;
         const int tail = std::min(W, 3);
-        const long long n_pre = 1ll << (2 * (W - tail));
-        dim3 grid((unsigned)((n_pre + 127) / 128), (unsigned)((n_cm + 15) / 16), 1);
-        if (tail == 3) smg::kmer_build_kernel<3><<<grid, 128, 0, st>>>(kp, W);
-        else if (tail == 2) smg::kmer_build_kernel<2><<<grid, 128, 0, st>>>(kp, W);
-        else smg::kmer_build_kernel<1><<<grid, 128, 0, st>>>(kp, W);
+        const int pre = W - tail;
+        // prefix levels walked depth first by one warp (4^sub leaves): as deep as leaves enough warps to fill the GPU
+        const long long tiles = (n_cm + smg::kBuildTile - 1) / smg::kBuildTile;
+        int sub = std::min(pre, 4);
+        while (sub > 1 && (1ll << (2 * (pre - sub))) * tiles < 148 * 32) --sub;
+        const long long n_sub = 1ll << (2 * (pre - sub));
+        dim3 grid((unsigned)((n_sub + 3) / 4), (unsigned)tiles, 1);
+        if (tail == 1) smg::kmer_build_kernel<0, 1><<<grid, 128, 0, st>>>(kp, W);
+        else if (tail == 2) smg::kmer_build_kernel<0, 2><<<grid, 128, 0, st>>>(kp, W);
+        else if (sub == 0) smg::kmer_build_kernel<0, 3><<<grid, 128, 0, st>>>(kp, W);
+        else if (sub == 1) smg::kmer_build_kernel<1, 3><<<grid, 128, 0, st>>>(kp, W);
+        else if (sub == 2) smg::kmer_build_kernel<2, 3><<<grid, 128, 0, st>>>(kp, W);
+        else if (sub == 3) smg::kmer_build_kernel<3, 3><<<grid, 128, 0, st>>>(kp, W);
+        else smg::kmer_build_kernel<4, 3><<<grid, 128, 0, st>>>(kp, W);
         ++*n_launches;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
