@@ -139,7 +139,7 @@ template <int SUB, int TAIL> struct KmerBuildDfs<SUB, SUB, TAIL> {
 
 // grid.x: subtrees (the first d0 = pre - SUB prefix bases), 4 per CTA; grid.y: tiles of 16 motifs of the class
 template <int SUB, int TAIL>
-__global__ void __launch_bounds__(128) kmer_build_kernel(const KmerParams kp, const int W)
+__global__ void __launch_bounds__(128) kmer_build_kernel(const __grid_constant__ KmerParams kp, const int W)
 {
     const ScanParams& p = kp.sp;
     __shared__ float s_tab[kBuildTile * kBuildRow];
@@ -287,7 +287,7 @@ __device__ __noinline__ void kmer_slow_window(const KmerParams& kp, const smg_ro
 }
 
 // dynamic shared memory: [2 * n_motifs] int histogram (hist_in_smem) -- counts of this chunk's row
-__global__ void __launch_bounds__(kKmerThreads, 3) scan_kmer_kernel(const KmerParams kp, const int hist_in_smem)
+__global__ void __launch_bounds__(kKmerThreads, 3) scan_kmer_kernel(const __grid_constant__ KmerParams kp, const int hist_in_smem)
 {
     const ScanParams& p = kp.sp;
     extern __shared__ int s_hist_dyn[];
@@ -323,13 +323,11 @@ __global__ void __launch_bounds__(kKmerThreads, 3) scan_kmer_kernel(const KmerPa
     const unsigned long long orow1 = (unsigned long long)(unsigned)p.out_rows[ch.row * 2 + 1] << key_shift;
     unsigned tallies[3] = {0, 0, 0};  // definite, near, accepted
     unsigned present = 0;
-    uint32_t hd32[kKmerMaxW + 1], bm32[kKmerMaxW + 1];  // 32-bit offsets of each class's heads / bitmap (the buffer has < 2^31 slots)
+    // (the per-class offsets kp.head_off[W] / kp.bm_off[W] are read from the constant bank where they are used: as
+    // arrays of registers they pushed the hot loop into local-memory spills -- 40 local accesses per 32 window starts)
 #pragma unroll
-    for (int W = 1; W <= kKmerMaxW; ++W) {
-        hd32[W] = (uint32_t)kp.head_off[W];
-        bm32[W] = (uint32_t)kp.bm_off[W];
+    for (int W = 1; W <= kKmerMaxW; ++W)
         if (W <= kp.max_w && kp.cls_off[W + 1] > kp.cls_off[W]) present |= 1u << W;
-    }
     const long long lim64 = (long long)row.g_len - (long long)row.g_off;
     const int lim = lim64 > 0x7fffffffll ? 0x7fffffff : (int)lim64;  // windows must end inside the sequence
     const int32_t* __restrict__ hd = kp.head;
@@ -373,7 +371,7 @@ __global__ void __launch_bounds__(kKmerThreads, 3) scan_kmer_kernel(const KmerPa
             bmw[W] = (ok >> W) & 1u;
             if (bmw[W]) {
                 const uint32_t x = win & (uint32_t)((1ull << (2 * W)) - 1ull);
-                if (W >= kKmerBitmapMinW) bmw[W] = (uint32_t)hd[bm32[W] + (x >> 5)] >> (x & 31);
+                if (W >= kKmerBitmapMinW) bmw[W] = (uint32_t)hd[(uint32_t)kp.bm_off[W] + (x >> 5)] >> (x & 31);
                 else bmw[W] = s_bm[kmer_sbm_off(W) + (x >> 5)] >> (x & 31);
             }
         }
@@ -381,7 +379,7 @@ __global__ void __launch_bounds__(kKmerThreads, 3) scan_kmer_kernel(const KmerPa
 #pragma unroll
         for (int W = 1; W <= kKmerMaxW; ++W) {
             heads[W] = -1;
-            if (bmw[W] & 1u) heads[W] = hd[hd32[W] + (win & (uint32_t)((1ull << (2 * W)) - 1ull))];
+            if (bmw[W] & 1u) heads[W] = hd[(uint32_t)kp.head_off[W] + (win & (uint32_t)((1ull << (2 * W)) - 1ull))];
         }
         // one list walk: every entry becomes a hit (or a tally, for k-mers the fp64 adjudicator rejected)
         auto walk = [&](int e, const int W, const int sp) {

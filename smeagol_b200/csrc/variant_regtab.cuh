@@ -36,7 +36,7 @@ struct VariantParams {
     }
 
 template <int WB>
-__global__ void __launch_bounds__(32) variant_regtab_kernel(const VariantParams vp)
+__global__ void __launch_bounds__(32) variant_regtab_kernel(const __grid_constant__ VariantParams vp)
 {
     using V = float2;
     const ScanParams& p = vp.sp;
@@ -199,7 +199,7 @@ __device__ __forceinline__ float vmax3(const float a, const float b, const float
 }
 
 template <int WB, bool FORK>
-__global__ void __launch_bounds__(32, (!FORK && WB == 12) ? 20 : 1) variant_tri_kernel(const VariantParams vp)
+__global__ void __launch_bounds__(32, (!FORK && WB == 12) ? 20 : 1) variant_tri_kernel(const __grid_constant__ VariantParams vp)
 {
     using V = float2;
     static_assert(2 * WB - 1 <= 32, "the fed bases must fit one 64-bit word");
