@@ -32,10 +32,43 @@ namespace smg {
 //     ub = ((acc + max_b T[W-3][b]) + max_b T[W-2][b]) + max_b T[W-1][b]      (fixed order, fp32, every step rounded)
 // -- an exact bound, not an estimate.  At hit densities of 1e-4 .. 6e-3 almost every prefix fails `ub > thr_lo` and its
 // 64 extensions are never formed; the survivors are expanded by the whole warp (lane = extension).
-__device__ __forceinline__ void kmer_emit_entry(const KmerParams& kp, const ScanParams& p, const int W, const long long x,
-                                                const float s, const float* tab, const int st, const int last, const int motif,
-                                                const float hi, const double t64, int32_t* head)
+// Warp-private allocation state of the index build.  Entry slots are reserved kSlotBlock at a time (ONE atomic round trip
+// per block; hits take their slots by ballot + prefix count), and the link of an entry -- the previous head returned by
+// atomicExch -- is stored one emission LATER, so that the round trip of the exchange overlaps the next expansion
+// instead of stalling the in-order warp (the build was latency-bound on exactly these two atomics).  The lists are only
+// read by the scan kernel, i.e. after this kernel has completed, so no ordering between entry and head is needed here.
+constexpr int kSlotBlock = 64;
+struct KmerBuildState {
+    unsigned long long slot_base;  // warp-uniform
+    int slot_used;                 // warp-uniform
+    long long pend_idx;            // per lane: entry whose `next` is still in flight (-1: none)
+    int pend_prev;
+};
+
+__device__ __forceinline__ void kmer_flush_link(const KmerParams& kp, KmerBuildState& bs)
 {
+    if (bs.pend_idx >= 0) kp.entries[bs.pend_idx].next = bs.pend_prev;
+    bs.pend_idx = -1;
+}
+
+// called by a converged warp; `hit` lanes append one entry each
+__device__ __forceinline__ void kmer_emit_entries(const KmerParams& kp, const ScanParams& p, KmerBuildState& bs, const bool hit,
+                                                  const int lane, const int W, const long long x, const float s, const float* tab,
+                                                  const int st, const int last, const int motif, const float hi, const double t64,
+                                                  int32_t* head)
+{
+    const unsigned hm = __ballot_sync(SMG_FULL_MASK, hit);
+    if (!hm) return;
+    const int n = __popc(hm);
+    if (bs.slot_used + n > kSlotBlock) {  // next block (the unused tail of the old one stays empty: never linked)
+        unsigned long long nb = 0;
+        if (lane == 0) nb = atomicAdd(&p.counters[SMG_CTR_KMER_ENTRIES], (unsigned long long)kSlotBlock);
+        bs.slot_base = __shfl_sync(SMG_FULL_MASK, nb, 0);
+        bs.slot_used = 0;
+    }
+    const unsigned long long idx = bs.slot_base + bs.slot_used + __popc(hm & ((1u << lane) - 1u));
+    bs.slot_used += n;
+    if (!hit) return;
     uint32_t flags = 0;
     if (!(s > hi)) {  // near-threshold band: decide in fp64 (same operands, same order)
         double a64 = 0.0;
@@ -46,12 +79,16 @@ __device__ __forceinline__ void kmer_emit_entry(const KmerParams& kp, const Scan
         }
         flags = kEntNear | ((a64 > t64) ? 0u : kEntRej);
     }
-    const unsigned long long idx = atomicAdd(&p.counters[SMG_CTR_KMER_ENTRIES], 1ull);
     if (idx < kp.entry_cap) {
+        kmer_flush_link(kp, bs);  // the previous exchange of this lane has long returned
         smg_kmer_entry_t e;
         e.col = (uint32_t)(motif * 2 + st) | flags;
         e.score = s;
-        e.next = atomicExch(&head[x], (int32_t)idx);
+        e.next = -1;
+        e.reserved = 0;
+        kp.entries[idx] = e;
+        bs.pend_prev = atomicExch(&head[x], (int32_t)idx);
+        bs.pend_idx = (long long)idx;
         atomicOr(reinterpret_cast<unsigned*>(kp.head + kp.bm_off[W]) + (x >> 5), 1u << (x & 31));
         if (W >= kKmerBitmapMinW && kp.max_w > kKmerBitmapMinW) {
             // combined bitmap of the wide classes, keyed by the max_w-mer: every extension of this k-mer
@@ -62,8 +99,6 @@ __device__ __forceinline__ void kmer_emit_entry(const KmerParams& kp, const Scan
                 atomicOr(cb + (y >> 5), 1u << (y & 31));
             }
         }
-        e.reserved = 0;
-        kp.entries[idx] = e;
     }
 }
 
@@ -87,7 +122,7 @@ struct KmerBuildCtx {
 };
 
 template <int TAIL>
-__device__ __forceinline__ void kmer_build_leaf(const KmerBuildCtx& c, const float acc, const long long q)
+__device__ __forceinline__ void kmer_build_leaf(const KmerBuildCtx& c, KmerBuildState& bs, const float acc, const long long q)
 {
     // exact upper bound of all 4^TAIL extensions (same chain of rounded additions, maxima as operands)
     float ub = (c.pre == 0) ? c.mx0 : __fadd_rn(acc, c.mx0);
@@ -103,7 +138,9 @@ __device__ __forceinline__ void kmer_build_leaf(const KmerBuildCtx& c, const flo
         const float lo = __shfl_sync(SMG_FULL_MASK, c.lo, src);
         const int t = src >> 1, st = src & 1;
         const float* tab = c.tab_all + t * kBuildRow;
-        for (int e = c.lane; e < kExt; e += 32) {
+#pragma unroll
+        for (int e0 = 0; e0 < kExt; e0 += 32) {
+            const int e = e0 + c.lane;
             float sc = a;
 #pragma unroll
             for (int u = 0; u < TAIL; ++u) {
@@ -111,29 +148,28 @@ __device__ __forceinline__ void kmer_build_leaf(const KmerBuildCtx& c, const flo
                 const float term = tab[st ? (c.last - j) : j];
                 sc = (c.pre + u == 0) ? term : __fadd_rn(sc, term);
             }
-            if (sc > lo)
-                kmer_emit_entry(*c.kp, c.kp->sp, c.W, q | ((long long)e << (2 * c.pre)), sc, tab, st, c.last, c.s_m[t], c.s_hi[t],
-                                c.s_t64[t], c.head);
+            kmer_emit_entries(*c.kp, c.kp->sp, bs, e < kExt && sc > lo, c.lane, c.W, q | ((long long)e << (2 * c.pre)), sc, tab, st,
+                              c.last, c.s_m[t], c.s_hi[t], c.s_t64[t], c.head);
         }
     }
 }
 
 template <int DEPTH, int SUB, int TAIL> struct KmerBuildDfs {
-    static __device__ __forceinline__ void run(const KmerBuildCtx& c, const float acc, const long long q)
+    static __device__ __forceinline__ void run(const KmerBuildCtx& c, KmerBuildState& bs, const float acc, const long long q)
     {
         const int k = c.d0 + DEPTH;
 #pragma unroll 1
         for (int b = 0; b < 4; ++b) {
             const int j = 4 * k + b;
             const float term = c.tab[c.st ? (c.last - j) : j];
-            KmerBuildDfs<DEPTH + 1, SUB, TAIL>::run(c, k == 0 ? term : __fadd_rn(acc, term), q | ((long long)b << (2 * k)));
+            KmerBuildDfs<DEPTH + 1, SUB, TAIL>::run(c, bs, k == 0 ? term : __fadd_rn(acc, term), q | ((long long)b << (2 * k)));
         }
     }
 };
 template <int SUB, int TAIL> struct KmerBuildDfs<SUB, SUB, TAIL> {
-    static __device__ __forceinline__ void run(const KmerBuildCtx& c, const float acc, const long long q)
+    static __device__ __forceinline__ void run(const KmerBuildCtx& c, KmerBuildState& bs, const float acc, const long long q)
     {
-        kmer_build_leaf<TAIL>(c, acc, q);
+        kmer_build_leaf<TAIL>(c, bs, acc, q);
     }
 };
 
@@ -190,7 +226,11 @@ __global__ void __launch_bounds__(128) kmer_build_kernel(const __grid_constant__
         const float term = c.tab[c.st ? (c.last - j) : j];
         acc = (k == 0) ? term : __fadd_rn(acc, term);
     }
-    KmerBuildDfs<0, SUB, TAIL>::run(c, acc, sub);
+    KmerBuildState bs;
+    bs.slot_base = 0; bs.slot_used = kSlotBlock;  // the first emission reserves a block
+    bs.pend_idx = -1; bs.pend_prev = -1;
+    KmerBuildDfs<0, SUB, TAIL>::run(c, bs, acc, sub);
+    kmer_flush_link(kp, bs);
 }
 
 // ---------------------------------------------------------------------------------------------------- scan
