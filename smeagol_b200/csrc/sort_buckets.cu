@@ -45,21 +45,38 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(const unsigned long
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned long long low_mask = (1ull << shift) - 1ull;
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    const unsigned long long n_round = (n + 31ull) & ~31ull;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        const bool have = i < n;
-        const unsigned long long k = have ? keys[i] : 0ull;
-        const unsigned b = have ? (unsigned)(k >> shift) : 0xffffffffu;
-        const unsigned m = __match_any_sync(SMG_FULL_MASK, b);
-        const int leader = __ffs((int)m) - 1;
-        unsigned base = 0;
-        if (have && (int)lane == leader) base = atomicAdd(&cursor[b], (unsigned)__popc(m));
-        base = __shfl_sync(SMG_FULL_MASK, base, leader);
-        if (have) {
-            const unsigned slot = base + (unsigned)__popc(m & lt_mask);
-            low[slot] = (uint32_t)(k & low_mask);
-            sc[slot] = scores[i];
+    // kU independent elements per thread and pass: the cursor atomics return a value, so with one element per pass
+    // every warp sat out a full L2 round trip per 32 hits (17 % issue utilisation); now kU round trips overlap
+    constexpr int kU = 4;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x * kU;
+    for (unsigned long long blk = (unsigned long long)blockIdx.x * blockDim.x * kU; blk < n; blk += stride) {  // CTA-uniform trips
+        const unsigned long long i0 = blk + threadIdx.x;
+        unsigned long long k[kU];
+        float v[kU];
+        unsigned base[kU], m[kU];
+        bool have[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const unsigned long long i = i0 + (unsigned long long)u * blockDim.x;
+            have[u] = i < n;
+            k[u] = have[u] ? keys[i] : 0ull;
+            v[u] = have[u] ? scores[i] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const unsigned b = have[u] ? (unsigned)(k[u] >> shift) : 0xffffffffu;
+            m[u] = __match_any_sync(SMG_FULL_MASK, b);
+            base[u] = 0;
+            if (have[u] && (int)lane == __ffs((int)m[u]) - 1) base[u] = atomicAdd(&cursor[b], (unsigned)__popc(m[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const unsigned bs = __shfl_sync(SMG_FULL_MASK, base[u], __ffs((int)m[u]) - 1);
+            if (have[u]) {
+                const unsigned slot = bs + (unsigned)__popc(m[u] & lt_mask);
+                low[slot] = (uint32_t)(k[u] & low_mask);
+                sc[slot] = v[u];
+            }
         }
     }
 }
