@@ -5,7 +5,7 @@
     python -m torch.distributed.run --nproc-per-node N ... bench_configs.py --config c3|c4   (STRONG scaling)
 
 c1  30 kb genome x 100 PWMs (W 7-12), both strands, thr 0.7 -- latency of the public scan_sequences() call
-c3  30 kb genome x 500 PWMs over 1,000 fixed pre-generated shuffled copies, counts only, backgrounds sharded
+c3  30 kb genome x 500 PWMs over 1,000 seeded dinucleotide-preserving shuffles (smg_kmer_shuffle), counts only, backgrounds sharded
     across ranks, one all_gather of the count tables
 c4  248 Mb sequence x 1,000 JASPAR-sized PWMs (W 6-24, mean 12), contiguous ranges + halo across ranks, hits stay
     rank-local (count + checksum), one all_reduce of the count table
@@ -108,10 +108,15 @@ def main():
         pw = synth.synth_pwms(500, 7, 12)
         model = PWMModel(pw)
         genome = synth.single_sequence(30_000, 3)
-        bgs = synth.mono_shuffles(genome, n_bg, seed=3)
         mine = sdist.shard_rows([30_000] * n_bg, world)[rank]
-        batch = dev.SeqBatch([bgs[i] for i in mine])
         n = len(mine)
+        # seeded DINUCLEOTIDE-preserving shuffles -- generated and packed on the device by smg_kmer_shuffle
+        # (utils.shuffle_batch_device, simK = 2), this rank's share with its own seed; they never exist on the host
+        import smeagol_b200 as sb
+        from smeagol_b200 import utils as sutils
+
+        rec = [sb.SeqRecord(sb.Seq(genome.tobytes().decode()), id="virus", name="virus")]
+        _, _, batch, _ = sutils.shuffle_batch_device(rec, n, simK=2, seed=3 + 1000 * rank, device=device)
         out_rows = np.stack([np.arange(n), n + np.arange(n)], axis=1).astype(np.int32)  # one group, rows [fwd.., rc..]
         plan = dev.ScanPlan(model.device_set, batch, model.thresholds(0.7), 3, out_rows, 2 * n, want_hits=False,
                             want_counts=True)
@@ -124,7 +129,7 @@ def main():
                 sdist.allgather_counts(plan.counts)
         units = n_bg * 30_000 * 500
         lookups = n_bg * 30_000 * 2 * int(model.device_set.widths.astype(np.int64).sum())
-        line = timed(step, units, {"config": {"workload": "c3: 30 kb genome x 500 PWMs x %d fixed shuffled copies, counts only (no site list), "
+        line = timed(step, units, {"config": {"workload": "c3: 30 kb genome x 500 PWMs x %d seeded dinucleotide-preserving shuffles (device-generated), counts only (no site list), "
                                                             "backgrounds sharded over ranks, one all_gather of count tables" % n_bg,
                                               "hits_counted_rank0": res.stats["n_hits_total"]}})
         line["roofline"] = {"bound": "fp32_pipe", "achieved": lookups / (line["ms_per_step"] * 1e-3) / 1e12 / world,
