@@ -124,6 +124,7 @@ def main():
         res = plan.finish()
 
         def step():
+            plan.launch_kmer_build()  # the per-call k-mer index belongs to the step
             plan.launch()
             if world > 1:
                 sdist.allgather_counts(plan.counts)
@@ -159,6 +160,7 @@ def main():
         total_counts = torch.zeros((1, M, 2), dtype=torch.int32, device=device)
 
         def step():
+            plan.launch_kmer_build()  # the per-call k-mer index belongs to the step
             plan.launch()
             total_counts.copy_(plan.counts.sum(dim=0, keepdim=True))
             sdist.allreduce_counts(total_counts)

@@ -63,40 +63,65 @@ def _locate_sites(encoding, model, thresholded, scores=None):
 _EMPTY_COUNTS = ["Matrix_id", "width", "id", "name", "sense", "num"]
 
 
-def _melt_counts(table, row_labels, model, extra=None):
-    """Sparse-crosstab semantics of scan._count_sites (scan.py:137-146): `table` is (n_rows, n_motifs) of counts for
-    one group; rows kept = PWMs with >=1 hit, columns kept = (id, name, sense) labels with >=1 hit; output iterates
-    sorted columns (outer) x sorted (Matrix_id, width) (inner)."""
+def _melt_counts_parts(table, row_labels, model):
+    """Index form of one group's melted crosstab: (m_idx, col_idx, labels, num) with labels = sorted unique
+    (id, name, sense) tuples; row j of the frame is PWM m_idx[j] x label col_idx[j] with count num[j].  None if empty."""
     ids, names, senses = row_labels
     table = _collapse_motifs(table, model, 1)
     # rows of the encoding sharing (id, name, sense) collapse into one crosstab column; columns are sorted tuples
     keys = list(zip(ids, names, senses))
     col_uniques = sorted(set(keys))
-    pos_of = {k: i for i, k in enumerate(col_uniques)}
-    col_codes = np.fromiter((pos_of[k] for k in keys), dtype=np.int64, count=len(keys))
     n_cols = len(col_uniques)
     if n_cols == len(keys):
-        agg = np.empty((n_cols, table.shape[1]), dtype=np.int64)
-        agg[col_codes] = table
+        if n_cols == 1:
+            agg = table.astype(np.int64, copy=False)
+        else:
+            pos_of = {k: i for i, k in enumerate(col_uniques)}
+            col_codes = np.fromiter((pos_of[k] for k in keys), dtype=np.int64, count=len(keys))
+            agg = np.empty((n_cols, table.shape[1]), dtype=np.int64)
+            agg[col_codes] = table
     else:
+        pos_of = {k: i for i, k in enumerate(col_uniques)}
+        col_codes = np.fromiter((pos_of[k] for k in keys), dtype=np.int64, count=len(keys))
         agg = np.zeros((n_cols, table.shape[1]), dtype=np.int64)
         np.add.at(agg, col_codes, table)
     keep_cols = np.flatnonzero(agg.sum(axis=1) > 0)
     keep_m = np.flatnonzero(agg.sum(axis=0) > 0)
     if keep_cols.size == 0:
-        return pd.DataFrame({k: [] for k in _EMPTY_COUNTS})
+        return None
     m_order = keep_m[np.argsort(_motif_rank(model)[keep_m], kind="stable")]
     sub = agg[np.ix_(keep_cols, m_order)]
-    nm = len(m_order)
-    rep = np.repeat(keep_cols, nm)
+    return np.tile(m_order, len(keep_cols)), np.repeat(keep_cols, len(m_order)), col_uniques, sub.reshape(-1)
+
+
+def _counts_frame(parts, model):
+    """ONE DataFrame for the melted crosstabs of many groups (in group order): a frame per group costs ~1 ms of pandas
+    overhead, which for 1,000 single-sequence groups was the whole cost of a `counts` call."""
+    parts = [p for p in parts if p is not None]
+    if not parts:
+        return pd.DataFrame({k: [] for k in _EMPTY_COUNTS})
+    labels, offs, base = [], [], 0
+    for _, _, lab, _ in parts:
+        offs.append(base)
+        labels.extend(lab)
+        base += len(lab)
+    m_idx = np.concatenate([p[0] for p in parts])
+    c_idx = np.concatenate([p[1] + o for p, o in zip(parts, offs)])
     return pd.DataFrame({
-        "Matrix_id": _take(model.Matrix_ids, np.tile(m_order, len(keep_cols))),
-        "width": np.tile(model.widths[m_order], len(keep_cols)),
-        "id": _take([c[0] for c in col_uniques], rep),
-        "name": _take([c[1] for c in col_uniques], rep),
-        "sense": _take([c[2] for c in col_uniques], rep),
-        "num": sub.reshape(-1),
+        "Matrix_id": _take(model.Matrix_ids, m_idx),
+        "width": model.widths[m_idx],
+        "id": _take([c[0] for c in labels], c_idx),
+        "name": _take([c[1] for c in labels], c_idx),
+        "sense": _take([c[2] for c in labels], c_idx),
+        "num": np.concatenate([p[3] for p in parts]),
     })
+
+
+def _melt_counts(table, row_labels, model, extra=None):
+    """Sparse-crosstab semantics of scan._count_sites (scan.py:137-146): `table` is (n_rows, n_motifs) of counts for
+    one group; rows kept = PWMs with >=1 hit, columns kept = (id, name, sense) labels with >=1 hit; output iterates
+    sorted columns (outer) x sorted (Matrix_id, width) (inner)."""
+    return _counts_frame([_melt_counts_parts(table, row_labels, model)], model)
 
 
 def _crosstab_rows(model):
@@ -310,8 +335,9 @@ def _find_sites_in_groups(encoding, model, threshold, outputs=["sites"], score=F
         if strands & 2:
             table[orow[:, 1]] = counts_dev[:, :, 1]
         gfo = layout["group_first_out"]
-        frames = [_melt_counts(table[gfo[gi]:gfo[gi + 1]], (g.ids, g.names, g.senses), model) for gi, g in enumerate(groups)]
-        counts = pd.concat(frames).reset_index(drop=True)
+        parts = [_melt_counts_parts(table[gfo[gi]:gfo[gi + 1]], (g.ids, g.names, g.senses), model) for gi, g in enumerate(groups)]
+        counts = _counts_frame(parts, model)
+        frames = [_counts_frame([pt], model) for pt in parts] if ("stats" in outputs and not combine_seqs) else None
         if "counts" in outputs or combine_seqs:
             output["counts"] = counts
         if "stats" in outputs and not combine_seqs:
