@@ -267,6 +267,16 @@ def test_melt_routes_with_inexact_edges_and_duplicate_pwm_keys():
     assert len(gotc) == len(wantc) == 4 * 4                      # 4 distinct (Matrix_id, width) keys x 4 label columns
     for col in wantc.columns:
         assert list(gotc[col]) == list(wantc[col]), col
+    # many groups in ONE frame (_counts_frame) == the per-group frames concatenated, incl. a group without any hit
+    groups = [(table[:2], (enc.ids[:2], enc.names[:2], enc.senses[:2])), (np.zeros((1, 6), dtype=np.int64), (["z"], ["z"], ["+"])),
+              (table[2:], (enc.ids[2:], enc.names[2:], enc.senses[2:]))]
+    one = sscan._counts_frame([sscan._melt_counts_parts(t, lab, model) for t, lab in groups], model)
+    per = pd.concat([sscan._melt_counts(t, lab, model) for t, lab in groups]).reset_index(drop=True)
+    assert list(one.columns) == list(per.columns) and len(one) == len(per) > 0
+    for col in per.columns:
+        assert list(one[col]) == list(per[col]), col
+    empty = sscan._counts_frame([None], model)
+    assert list(empty.columns) == ["Matrix_id", "width", "id", "name", "sense", "num"] and len(empty) == 0
 
 
 def test_device_seq_behaves_like_a_seq():
