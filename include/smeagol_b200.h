@@ -279,6 +279,22 @@ int smg_variant_windows_mode(smg_pwmset_t set, const uint32_t* d_packed, const u
                              const uint8_t* d_snv_alt, int64_t n_snv, float* d_ref_max, float* d_alt_max, int32_t exact,
                              int32_t motif_major, void* stream);
 
+/* SEED ENGINE for the PWMs of the tensor-core side (same contract as smg_scan_tc5: exact second pass, identical results).
+ * A window of a PWM of width W can only be a hit if its most selective seed_len consecutive positions score more than
+ * threshold - (maximum of the remaining positions); every (PWM, strand) becomes a forward-only virtual PWM of width
+ * seed_len in a one-class k-mer index built per call, and the scan turns every list entry into a candidate window that
+ * finalize re-scores.  smg_seed_prepare: info[0] = virtual PWMs, info[1] = int32 slots of the index buffer (d_head),
+ * info[2] = largest seed offset, info[3] = 1 if every PWM of the tensor-core side is seedable (W <= seed_len + 12). */
+int smg_seed_prepare(smg_pwmset_t set, int seed_len, int64_t info[4]);
+int smg_seed_index_build(smg_pwmset_t set, int seed_len, int strands, const float* d_thr_lo, int32_t* d_head, int64_t head_len,
+                         smg_kmer_entry_t* d_entries, uint64_t entry_cap, uint64_t* d_counters, void* stream);
+int smg_scan_seed(smg_pwmset_t set, int seed_len, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
+                  const smg_row_t* d_rows, int32_t n_rows, const int32_t* d_out_rows, const smg_chunk_t* d_chunks,
+                  int32_t n_chunks, int32_t chunk_len, int strands, const float* d_thr_lo, const float* d_thr_hi,
+                  const double* d_thr64, int pos_bits, int motif_bits, int cand_pos_bits, const int32_t* d_head,
+                  const smg_kmer_entry_t* d_entries, uint64_t* d_cand, uint64_t cand_cap, uint64_t* d_hit_keys,
+                  float* d_hit_scores, uint64_t hit_cap, int32_t* d_counts, uint64_t* d_counters, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,7 +18,7 @@ NEAR_BYTES = 24
 # every symbol include/smeagol_b200.h declares (tests/test_cabi.py checks the export list against the header)
 EXPORTS = [
     "smg_version", "smg_last_error", "smg_launch_count", "smg_pwmset_create", "smg_pwmset_create_split", "smg_pwmset_create_split3",
-    "smg_kmer_index_size", "smg_kmer_index_build", "smg_scan_kmer", "smg_pwmset_destroy", "smg_pwmset_info",
+    "smg_kmer_index_size", "smg_kmer_index_build", "smg_scan_kmer", "smg_seed_prepare", "smg_seed_index_build", "smg_scan_seed", "smg_pwmset_destroy", "smg_pwmset_info",
     "smg_pack", "smg_scan", "smg_scan_tc", "smg_scan_tc5", "smg_adjudicate", "smg_sort_hits", "smg_sort_hits_bucketed", "smg_predict_dense", "smg_variant_sites",
     "smg_variant_windows", "smg_variant_windows_mode", "smg_pairwise_ncorrs", "smg_window_counts", "smg_fasta_index", "smg_fasta_compact", "smg_kmer_shuffle", "smg_bin_hits",
 ]
@@ -60,6 +60,10 @@ def load():
     lib.smg_scan_tc.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int,
                                 ctypes.c_int, ctypes.c_int, vp, u64, vp, vp, u64, vp, vp, vp]
     lib.smg_scan_tc5.argtypes = lib.smg_scan_tc.argtypes
+    lib.smg_seed_prepare.argtypes = [vp, ctypes.c_int, vp]
+    lib.smg_seed_index_build.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, i64, vp, u64, vp, vp]
+    lib.smg_scan_seed.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, i32, vp, vp, i32, i32, ctypes.c_int, vp, vp, vp, ctypes.c_int,
+                                  ctypes.c_int, ctypes.c_int, vp, vp, vp, u64, vp, vp, u64, vp, vp, vp]
     lib.smg_pairwise_ncorrs.argtypes = [vp, vp, vp, i32, vp, vp]
     lib.smg_window_counts.argtypes = [vp, u64, ctypes.c_int, ctypes.c_int, vp, vp, vp, i64, i64, vp, vp]
     lib.smg_bin_hits.argtypes = [vp, vp, u64, ctypes.c_int, ctypes.c_int, vp, vp, i32, i32, vp, vp]

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -91,6 +92,17 @@ struct smg_pwmset {
     int32_t* d_t5_col_id = nullptr;
     float* d_t5_thr_pre_col = nullptr;
     int64_t sum_padded = 0;
+    // seed engine (kmer.h): per seed length S, the virtual forward-only PWMs of the tensor-core side's (PWM, strand) columns
+    struct SeedSet {
+        int S = 0, nv = 0, o_max = 0;
+        bool eligible = false;  // every PWM of the tensor-core side satisfies W <= S + kSeedMaxRest
+        std::vector<int> widths;  // nv x S (layout of the one-class index)
+        float* d_vtab = nullptr; int64_t* d_voff = nullptr; int32_t* d_vwidth = nullptr; int32_t* d_vcol = nullptr;
+        int32_t* d_voffset = nullptr; float* d_vrest = nullptr; float* d_vthr = nullptr; double* d_vthr64 = nullptr;
+        int32_t* d_cls = nullptr;
+    };
+    std::map<int, SeedSet*> seeds;
+    std::vector<float> h_nat;  // host copy of the natural tables (seed selection)
     float* d_nat = nullptr;
     int32_t* d_width = nullptr;
     int64_t* d_off = nullptr;
@@ -784,6 +796,7 @@ int smg_pwmset_create_split3(const float* h_weights, const int32_t* h_widths, in
     std::vector<int32_t> widev(s->wide.begin(), s->wide.end());
     for (int m = 0; m < n_motifs; ++m) (h_widths[m] <= kDualMaxWidth ? s->dual_motifs : s->nondual_motifs).push_back(m);
     std::vector<int32_t> dualv(s->dual_motifs.begin(), s->dual_motifs.end()), nondualv(s->nondual_motifs.begin(), s->nondual_motifs.end());
+    s->h_nat = nat;
     if ((rc = upload(&s->d_nat, nat)) || (rc = upload(&s->d_width, wv)) || (rc = upload(&s->d_off, s->offs)) ||
         (rc = upload(&s->d_gtab, gtab)) || (rc = upload(&s->d_gtab_off, gtab_off)) ||
         (rc = upload(&s->d_lane_motif, lane_motif)) ||
@@ -807,6 +820,12 @@ int smg_pwmset_destroy(smg_pwmset_t s)
     if (!s) return SMG_OK;
     cudaFree(s->d_nat); cudaFree(s->d_width); cudaFree(s->d_off); cudaFree(s->d_gtab); cudaFree(s->d_gtab_off);
     cudaFree(s->d_cls_motifs);
+    for (auto& kv : s->seeds) {
+        smg_pwmset::SeedSet* q = kv.second;
+        cudaFree(q->d_vtab); cudaFree(q->d_voff); cudaFree(q->d_vwidth); cudaFree(q->d_vcol); cudaFree(q->d_voffset);
+        cudaFree(q->d_vrest); cudaFree(q->d_vthr); cudaFree(q->d_vthr64); cudaFree(q->d_cls);
+        delete q;
+    }
     cudaFree(s->d_t5_img); cudaFree(s->d_t5_cg_img_off); cudaFree(s->d_t5_cg_first_blk); cudaFree(s->d_t5_blk_ks);
     cudaFree(s->d_t5_blk_off); cudaFree(s->d_t5_col_id); cudaFree(s->d_t5_thr_pre_col);
     cudaFree(s->d_lane_motif); cudaFree(s->d_afrag); cudaFree(s->d_cg_afrag_off); cudaFree(s->d_col_id); cudaFree(s->d_thr_pre_col); cudaFree(s->d_wide); cudaFree(s->d_dual_list); cudaFree(s->d_nondual_list);
@@ -1007,6 +1026,182 @@ int smg_scan_tc5(smg_pwmset_t s, const uint32_t* d_packed, const uint16_t* d_ama
     ++g_launches;
     finalize_candidates_kernel<<<148 * SMG_FINALIZE_MIN_BLOCKS * 2, 256, 0, st>>>(p, reinterpret_cast<const unsigned long long*>(d_cand), cand_cap,
                                                        hp.cand_shift, d_thr64);
+    SMG_LAUNCH_CHECK("finalize_candidates_kernel");
+    return SMG_OK;
+}
+
+// ------------------------------------------------------------------------------------------ seed engine (kmer.h)
+static smg_pwmset::SeedSet* seed_set(smg_pwmset_t s, const int S)
+{
+    auto it = s->seeds.find(S);
+    if (it != s->seeds.end()) return it->second;
+    smg_pwmset::SeedSet* q = new smg_pwmset::SeedSet();
+    q->S = S;
+    q->eligible = s->split > 0;
+    std::vector<float> vtab;
+    std::vector<int64_t> voff;
+    std::vector<int32_t> vwidth, vcol, voffset, cls;
+    std::vector<float> vrest;
+    for (int m = 0; m < s->n_motifs; ++m) {
+        const int W = s->widths[m];
+        if (!(s->split > 0 && W >= s->split && W >= s->kmin && W <= SMG_MAX_REGTAB_WIDTH)) continue;  // the tensor-core side
+        if (W <= S || W > S + smg::kSeedMaxRest) { q->eligible = false; continue; }
+        const float* T = s->h_nat.data() + s->offs[m] * 4;
+        for (int st = 0; st < 2; ++st) {
+            // strand table on the forward string: T[k][b] or Trc[k][b] = T[W-1-k][3-b]
+            auto at = [&](int k, int b) { return st ? T[(W - 1 - k) * 4 + (3 - b)] : T[k * 4 + b]; };
+            std::vector<double> mx(W), mu(W), var(W), amx(W);
+            double sum_mx = 0.0, sum_abs = 0.0, thr_proxy = 0.0;
+            for (int k = 0; k < W; ++k) {
+                double a = -1e300, m1 = 0.0, m2 = 0.0, ab = 0.0;
+                for (int b = 0; b < 4; ++b) {
+                    const double v = std::isfinite(at(k, b)) ? (double)at(k, b) : -60000.0;
+                    a = std::max(a, v); m1 += v; m2 += v * v; ab = std::max(ab, std::fabs(v));
+                }
+                thr_proxy += a;
+                mx[k] = std::max(a, 0.0);  // 'Z' / padding contribute 0: the rest is bounded by max(0, max_b T)
+                mu[k] = m1 / 4; var[k] = std::max(m2 / 4 - mu[k] * mu[k], 1e-12); amx[k] = ab;
+                sum_mx += mx[k]; sum_abs += ab;
+            }
+            // the most selective S consecutive positions: largest z-score of the seed threshold (thr ~ 0.7 x max score)
+            int best_o = 0;
+            double best_z = -1e300;
+            for (int o = 0; o + S <= W; ++o) {
+                double smx = 0.0, smu = 0.0, sv = 0.0;
+                for (int k = o; k < o + S; ++k) { smx += mx[k]; smu += mu[k]; sv += var[k]; }
+                const double z = (0.7 * thr_proxy - (sum_mx - smx) - smu) / std::sqrt(sv);
+                if (z > best_z) { best_z = z; best_o = o; }
+            }
+            double rest = 0.0;
+            for (int k = 0; k < W; ++k)
+                if (k < best_o || k >= best_o + S) rest += mx[k];
+            voff.push_back((int64_t)vcol.size() * S);
+            cls.push_back((int32_t)vcol.size());
+            vcol.push_back(m * 2 + st);
+            vwidth.push_back(S);
+            voffset.push_back(best_o);
+            // margin: fp32 rounding of both sums (<< 2^-16 x the score scale) + a constant
+            vrest.push_back((float)(rest + 1e-3 + sum_abs * (1.0 / 65536.0)) * 1.000001f);
+            for (int k = best_o; k < best_o + S; ++k)
+                for (int b = 0; b < 4; ++b) vtab.push_back(at(k, b));
+            q->o_max = std::max(q->o_max, best_o);
+        }
+    }
+    q->nv = (int)vcol.size();
+    q->widths.assign(q->nv, S);
+    if (q->nv == 0) q->eligible = false;
+    std::vector<float> vthr(std::max(q->nv, 1), 0.f);
+    std::vector<double> vthr64(std::max(q->nv, 1), 0.0);
+    if (upload(&q->d_vtab, vtab) || upload(&q->d_voff, voff) || upload(&q->d_vwidth, vwidth) || upload(&q->d_vcol, vcol) ||
+        upload(&q->d_voffset, voffset) || upload(&q->d_vrest, vrest) || upload(&q->d_vthr, vthr) || upload(&q->d_vthr64, vthr64) ||
+        upload(&q->d_cls, cls)) {
+        delete q;
+        return nullptr;
+    }
+    s->seeds[S] = q;
+    return q;
+}
+
+// seed thresholds of a call: thr_lo of the real PWM minus the bound of the rest of the window; +inf switches a strand off
+__global__ void seed_thr_kernel(const int32_t* __restrict__ vcol, const float* __restrict__ vrest, const float* __restrict__ thr_lo,
+                                const int strands, const int nv, float* __restrict__ vthr)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    const int col = vcol[v];
+    vthr[v] = ((strands >> (col & 1)) & 1) ? thr_lo[col >> 1] - vrest[v] : __int_as_float(0x7f800000);
+}
+
+int smg_seed_prepare(smg_pwmset_t s, int seed_len, int64_t info[4])
+{
+    if (!s || !info || seed_len < 4 || seed_len > SMG_KMER_MAX_WIDTH) return fail(SMG_ERR_INVALID, "smg_seed_prepare: bad argument");
+    smg_pwmset::SeedSet* q = seed_set(s, seed_len);
+    if (!q) return fail(SMG_ERR_CUDA, "smg_seed_prepare: out of memory");
+    info[0] = q->nv;
+    info[1] = q->nv ? smg_kmer_head_len(q->widths, seed_len) : 0;
+    info[2] = q->o_max;
+    info[3] = q->eligible ? 1 : 0;
+    return SMG_OK;
+}
+
+static int seed_kmer_params(smg::KmerParams& kp, smg_pwmset::SeedSet* q, int32_t* d_head, smg_kmer_entry_t* d_entries,
+                            uint64_t entry_cap, uint64_t* d_counters)
+{
+    memset(&kp, 0, sizeof(kp));
+    kp.sp.n_motifs = q->nv; kp.sp.motif_width = q->d_vwidth; kp.sp.motif_off = q->d_voff; kp.sp.nat_tab = q->d_vtab;
+    kp.sp.strands = 1; kp.sp.thr_lo = q->d_vthr; kp.sp.thr_hi = q->d_vthr;  // forward-only virtual PWMs, no near band
+    kp.sp.counters = reinterpret_cast<unsigned long long*>(d_counters);
+    if (smg_kmer_fill_params(kp, q->widths, q->d_cls, q->S)) return 1;
+    kp.head = d_head; kp.entries = d_entries; kp.entry_cap = entry_cap; kp.thr64 = q->d_vthr64;
+    return 0;
+}
+
+int smg_seed_index_build(smg_pwmset_t s, int seed_len, int strands, const float* d_thr_lo, int32_t* d_head, int64_t head_len,
+                         smg_kmer_entry_t* d_entries, uint64_t entry_cap, uint64_t* d_counters, void* stream)
+{
+    if (!s || !d_thr_lo || !d_head || !d_entries || entry_cap == 0 || entry_cap > 0x7fffffffull || !d_counters)
+        return fail(SMG_ERR_INVALID, "smg_seed_index_build: bad argument");
+    if ((strands & 3) == 0 || (strands & ~3)) return fail(SMG_ERR_INVALID, "smg_seed_index_build: strands must be 1, 2 or 3");
+    smg_pwmset::SeedSet* q = seed_set(s, seed_len);
+    if (!q || q->nv == 0) return fail(SMG_ERR_INVALID, "smg_seed_index_build: no seeded PWMs (smg_seed_prepare)");
+    if (head_len != smg_kmer_head_len(q->widths, seed_len)) return fail(SMG_ERR_INVALID, "smg_seed_index_build: head_len mismatch");
+    cudaStream_t st = (cudaStream_t)stream;
+    seed_thr_kernel<<<(q->nv + 255) / 256, 256, 0, st>>>(q->d_vcol, q->d_vrest, d_thr_lo, strands, q->nv, q->d_vthr);
+    SMG_LAUNCH_CHECK("seed_thr_kernel");
+    smg::KmerParams kp;
+    if (seed_kmer_params(kp, q, d_head, d_entries, entry_cap, d_counters)) return fail(SMG_ERR_INVALID, "smg_seed_index_build: bad seed length");
+    int64_t n_heads = 0;
+    smg_kmer_head_len(q->widths, seed_len, &n_heads);
+    SMG_CUDA(cudaMemsetAsync(d_head, 0xff, (size_t)n_heads * sizeof(int32_t), st));
+    SMG_CUDA(cudaMemsetAsync(d_head + n_heads, 0, (size_t)(head_len - n_heads) * sizeof(int32_t), st));
+    uint64_t nl = 0;
+    cudaError_t e = smg_kmer_launch_build(kp, st, &nl);
+    g_launches += nl;
+    if (e != cudaSuccess) return fail(SMG_ERR_CUDA, std::string("kmer_build_kernel (seeds): ") + cudaGetErrorString(e));
+    return SMG_OK;
+}
+
+int smg_scan_seed(smg_pwmset_t s, int seed_len, const uint32_t* d_packed, const uint16_t* d_amask, const uint8_t* d_codes,
+                  const smg_row_t* d_rows, int32_t n_rows, const int32_t* d_out_rows, const smg_chunk_t* d_chunks, int32_t n_chunks,
+                  int32_t chunk_len, int strands, const float* d_thr_lo, const float* d_thr_hi, const double* d_thr64, int pos_bits,
+                  int motif_bits, int cand_pos_bits, const int32_t* d_head, const smg_kmer_entry_t* d_entries, uint64_t* d_cand,
+                  uint64_t cand_cap, uint64_t* d_hit_keys, float* d_hit_scores, uint64_t hit_cap, int32_t* d_counts,
+                  uint64_t* d_counters, void* stream)
+{
+    if (!s || !d_packed || !d_amask || !d_rows || n_rows <= 0 || !d_out_rows || !d_chunks || n_chunks < 0 || !d_thr_lo ||
+        !d_thr_hi || !d_thr64 || !d_counters || !d_cand || cand_cap == 0 || !d_head || !d_entries)
+        return fail(SMG_ERR_INVALID, "smg_scan_seed: bad argument");
+    if (chunk_len <= 0 || (chunk_len & 15)) return fail(SMG_ERR_INVALID, "smg_scan_seed: chunk_len must be a positive multiple of 16");
+    if ((strands & 3) == 0 || (strands & ~3)) return fail(SMG_ERR_INVALID, "smg_scan_seed: strands must be 1, 2 or 3");
+    if (pos_bits <= 0 || motif_bits <= 0 || pos_bits + motif_bits > 63) return fail(SMG_ERR_INVALID, "smg_scan_seed: bad key layout");
+    if ((1ll << motif_bits) < s->n_motifs) return fail(SMG_ERR_INVALID, "smg_scan_seed: motif_bits too small");
+    if (cand_pos_bits <= 0 || cand_pos_bits + motif_bits + 1 > 62) return fail(SMG_ERR_INVALID, "smg_scan_seed: bad candidate layout");
+    if ((d_hit_keys == nullptr) != (d_hit_scores == nullptr)) return fail(SMG_ERR_INVALID, "smg_scan_seed: hit buffers must both be set or NULL");
+    smg_pwmset::SeedSet* q = seed_set(s, seed_len);
+    if (!q || q->nv == 0 || !q->eligible) return fail(SMG_ERR_INVALID, "smg_scan_seed: the PWM set is not eligible for seeding at this length");
+    if (n_chunks == 0) return SMG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    ScanParams p;
+    fill_params(p, s, d_packed, d_amask, d_codes, d_rows, d_out_rows);
+    p.chunks = d_chunks; p.chunk_len = chunk_len; p.strands = strands; p.thr_lo = d_thr_lo; p.thr_hi = d_thr_hi;
+    p.pos_bits = pos_bits; p.motif_bits = motif_bits;
+    p.hit_keys = reinterpret_cast<unsigned long long*>(d_hit_keys); p.hit_scores = d_hit_scores; p.hit_cap = hit_cap;
+    p.counts = d_counts; p.counters = reinterpret_cast<unsigned long long*>(d_counters);
+    smg::KmerParams kp;
+    if (seed_kmer_params(kp, q, const_cast<int32_t*>(d_head), const_cast<smg_kmer_entry_t*>(d_entries), 1, d_counters))
+        return fail(SMG_ERR_INVALID, "smg_scan_seed: bad seed length");
+    smg::SeedParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.sp = p; sp.head = d_head; sp.head_off = kp.head_off[q->S]; sp.bm_off = kp.bm_off[q->S]; sp.entries = d_entries;
+    sp.vcol = q->d_vcol; sp.voffset = q->d_voffset; sp.vtab = q->d_vtab; sp.vthr = q->d_vthr;
+    sp.nv = q->nv; sp.S = q->S; sp.o_max = q->o_max; sp.n_chunks = n_chunks;
+    sp.cand_shift = cand_pos_bits + motif_bits + 1;
+    sp.cand = reinterpret_cast<unsigned long long*>(d_cand); sp.cand_cap = cand_cap;
+    cudaError_t e = smg_seed_launch_scan(sp, st);
+    if (e != cudaSuccess) return fail(SMG_ERR_CUDA, std::string("seed_scan_kernel: ") + cudaGetErrorString(e));
+    ++g_launches;
+    finalize_candidates_kernel<<<148 * SMG_FINALIZE_MIN_BLOCKS * 2, 256, 0, st>>>(p, reinterpret_cast<const unsigned long long*>(d_cand), cand_cap,
+                                                       sp.cand_shift, d_thr64);
     SMG_LAUNCH_CHECK("finalize_candidates_kernel");
     return SMG_OK;
 }

@@ -500,6 +500,108 @@ __global__ void __launch_bounds__(kKmerThreads, 3) scan_kmer_kernel(const __grid
     }
 }
 
+// ---------------------------------------------------------------------------------------------------- seed scan
+// One thread = one seed position q.  Clean S-mers: bitmap probe, head, list walk; every entry is a virtual PWM whose
+// window starts at q - offset and becomes a 64-bit candidate for finalize_candidates_kernel (exact fp32 / fp64 scoring).
+// S-mers with IUPAC codes cannot be looked up: the thread scores the soft seed of every virtual PWM directly (rare).
+// A window is owned by the row segment that contains its START: the last chunk of a row also visits the o_max seed
+// positions beyond its owned starts, and candidates whose start falls outside [0, n_own) are dropped.
+struct SeedStage {
+    unsigned long long c[256];
+    int n;
+};
+
+__device__ __forceinline__ void seed_push(const SeedParams& sp, SeedStage* stg, const unsigned long long cand)
+{
+    const int slot = atomicAdd(&stg->n, 1);
+    if (slot < 256) {
+        stg->c[slot] = cand;
+    } else {  // stage full (long lists / the slow path): straight to the global list
+        const unsigned long long idx = atomicAdd(&sp.sp.counters[SMG_CTR_CANDIDATES], 1ull);
+        if (idx < sp.cand_cap) sp.cand[idx] = cand;
+    }
+}
+
+__device__ __forceinline__ void seed_flush(const SeedParams& sp, SeedStage* stg, const int lane)
+{
+    __syncwarp();
+    const int n = min(stg->n, 256);
+    if (n > 0) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&sp.sp.counters[SMG_CTR_CANDIDATES], (unsigned long long)n);
+        base = __shfl_sync(SMG_FULL_MASK, base, 0);
+        for (int i = lane; i < n; i += 32)
+            if (base + i < sp.cand_cap) sp.cand[base + i] = stg->c[i];
+    }
+    __syncwarp();
+    if (lane == 0) stg->n = 0;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(256) seed_scan_kernel(const __grid_constant__ SeedParams sp)
+{
+    const ScanParams& p = sp.sp;
+    __shared__ SeedStage s_stage[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    SeedStage* stg = &s_stage[warp];
+    if (lane == 0) stg->n = 0;
+    __syncwarp();
+    const smg_chunk_t ch = p.chunks[blockIdx.x];
+    const smg_row_t row = p.rows[ch.row];
+    const int c0 = ch.start, c1 = min(c0 + p.chunk_len, row.n_own);
+    if (c1 <= c0) return;
+    const int S = sp.S;
+    // seed positions of this chunk; the row's last chunk also covers the seeds of windows that start just before n_own
+    const int q_last = min((c1 == row.n_own) ? c1 + sp.o_max : c1, row.n_avail - S + 1);  // exclusive
+    const uint32_t* __restrict__ wp = p.packed + row.word_off;
+    const uint16_t* __restrict__ ap = p.amask + row.word_off;
+    const uint32_t kmask = (uint32_t)((1ull << (2 * S)) - 1ull), amask_s = (1u << S) - 1u;
+    const int32_t* __restrict__ hd = sp.head;
+    const unsigned long long rowbits = (unsigned long long)(unsigned)ch.row << sp.cand_shift;
+    const int pos_shift = p.motif_bits + 1;
+    for (int qb = c0 + warp * 32; qb < q_last; qb += 256) {
+        const int q = qb + lane;
+        if (q < q_last) {
+            const int w = q >> 4, sh = q & 15;
+            const uint32_t p0 = wp[w], p1 = wp[w + 1];
+            const uint32_t a0 = ap[w], a1 = ap[w + 1];
+            const uint32_t x = __funnelshift_r(p0, p1, 2 * sh) & kmask;
+            const uint32_t am = ((a0 | (a1 << 16)) >> sh) & amask_s;
+            if (am == 0u) {
+                if (((uint32_t)hd[sp.bm_off + (x >> 5)] >> (x & 31)) & 1u) {
+                    int e = hd[sp.head_off + x];
+                    while (e >= 0) {
+                        const smg_kmer_entry_t ent = sp.entries[e];
+                        e = ent.next;
+                        const int v = (int)((ent.col & 0x1fffffffu) >> 1);
+                        const int start = q - sp.voffset[v];
+                        if (start >= 0 && start < row.n_own)
+                            seed_push(sp, stg, rowbits | ((unsigned long long)(unsigned)start << pos_shift) | (unsigned long long)(unsigned)sp.vcol[v]);
+                    }
+                }
+            } else {
+                // soft one-hot seed (encode.py:11-29) of every virtual PWM, any summation order: the threshold carries a margin
+                for (int v = 0; v < sp.nv; ++v) {
+                    const int start = q - sp.voffset[v];
+                    if (start < 0 || start >= row.n_own) continue;
+                    const float* tab = sp.vtab + (size_t)v * S * 4;
+                    float acc = 0.f;
+                    for (int k = 0; k < S; ++k) {
+                        const int c = smg_fetch_code(p.packed, p.amask, p.codes, row, (int64_t)q + k);
+                        acc += smg_mix(c_emb[c][0], c_emb[c][1], c_emb[c][2], c_emb[c][3], tab[4 * k], tab[4 * k + 1], tab[4 * k + 2],
+                                       tab[4 * k + 3]);
+                    }
+                    if (acc > sp.vthr[v])
+                        seed_push(sp, stg, rowbits | ((unsigned long long)(unsigned)start << pos_shift) | (unsigned long long)(unsigned)sp.vcol[v]);
+                }
+            }
+        }
+        __syncwarp();
+        if (stg->n > 128) seed_flush(sp, stg, lane);
+    }
+    seed_flush(sp, stg, lane);
+}
+
 }  // namespace smg
 
 // ---------------------------------------------------------------------------------------------------- host side
@@ -569,6 +671,12 @@ cudaError_t smg_kmer_launch_build(const smg::KmerParams& kp, cudaStream_t st, ui
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
+}
+
+cudaError_t smg_seed_launch_scan(const smg::SeedParams& sp, cudaStream_t st)
+{
+    smg::seed_scan_kernel<<<(unsigned)sp.n_chunks, 256, 0, st>>>(sp);
+    return cudaGetLastError();
 }
 
 cudaError_t smg_kmer_launch_scan(const smg::KmerParams& kp, int n_chunks, cudaStream_t st)

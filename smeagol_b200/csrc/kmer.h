@@ -40,8 +40,28 @@ struct KmerParams {
     const double* thr64;
 };
 
+// ---- seed engine (wide PWMs through the k-mer machinery): a window of a PWM of width W > S can only be a hit if its
+// most selective S consecutive positions (the SEED, at offset o of the window) score more than thr - (maximum of the
+// rest); every (PWM, strand) becomes a VIRTUAL forward-only PWM of width S in a one-class k-mer index built per call.
+constexpr int kSeedMaxRest = 12;  // a PWM is seeded when W <= S + kSeedMaxRest
+struct SeedParams {
+    ScanParams sp;                 // the REAL PWM set (rows, chunks, candidate key layout)
+    const int32_t* head;           // one-class index of the virtual PWMs
+    int64_t head_off, bm_off;      // heads / bitmap of class S inside `head`
+    const smg_kmer_entry_t* entries;
+    const int32_t* vcol;           // [nv] real motif * 2 + strand
+    const int32_t* voffset;        // [nv] offset of the seed inside the window
+    const float* vtab;             // [nv][S][4] seed tables (strand already applied)
+    const float* vthr;             // [nv] seed thresholds of this call
+    int32_t nv, S, o_max, n_chunks;
+    int32_t cand_shift;            // candidate = row << cand_shift | start << (motif_bits + 1) | motif << 1 | strand
+    unsigned long long* cand;
+    unsigned long long cand_cap;
+};
+
 }  // namespace smg
 
+cudaError_t smg_seed_launch_scan(const smg::SeedParams& sp, cudaStream_t st);
 int smg_kmer_fill_params(smg::KmerParams& kp, const std::vector<int>& widths, const int32_t* d_cls_motifs, int max_w);
 // int32 slots of the index buffer: list heads of every class, then the bitmaps; *n_heads = the head part
 int64_t smg_kmer_head_len(const std::vector<int>& widths, int max_w, int64_t* n_heads = nullptr);

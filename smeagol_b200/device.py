@@ -20,6 +20,7 @@ NEAR_REL = 1e-5     # half-width of the near-threshold band, relative to sum_k m
 STRANDS = {"none": 1, "only": 2, "both": 3}
 DEFAULT_ENGINE = "regtab"
 DEFAULT_TC_KIND = "tc5"
+SEED_MIN_LEN = 10     # the seed engine replaces the tensor-core prefilter when the k-mer index reaches this width
 KMER_MAX_WIDTH = 12   # widest class of the k-mer index engine (csrc/kmer.cu)
 KMER_ALPHA = 1.5     # a width class joins the k-mer index when 4^W <= KMER_ALPHA * window starts (break-even of index build vs tcgen05 scan, profiles/r02_bench_widths.txt)
                       # k-mers once costs about as much per (k-mer, PWM) as any engine spends per (position, PWM)  # tensor-core prefilter of the 'auto' / tensor-core engines: 'hmma' (mma.sync) or 'tc5' (tcgen05 + TMEM)
@@ -312,6 +313,7 @@ class ScanPlan:
             self.engine = "regtab"  # PWMs wider than 32 only exist in the register-table / generic path
         # ---- k-mer index engine for the narrow width classes (engine 'auto' only)
         self.kmer_w = 0
+        self.seed_len = 0
         if self.engine == "auto" and os.environ.get("SMEAGOL_B200_KMER", "1") != "0":
             forced = os.environ.get("SMEAGOL_B200_KMER_MAX_WIDTH")
             wk = 0
@@ -324,6 +326,16 @@ class ScanPlan:
             present = present[present <= wk]
             self.kmer_w = int(present.max()) if present.size else 0
             pwmset = pwmset.with_kmer(self.kmer_w)
+            # ---- seed engine: when the scan is long enough for a 10..12-mer index, the wide PWMs go through it too
+            # (seed = their most selective kmer_w positions, csrc/kmer.h) instead of the tensor-core prefilter
+            self.seed_len = 0
+            if (wk >= SEED_MIN_LEN and self.kmer_w > 0 and os.environ.get("SMEAGOL_B200_SEED", "1") != "0"
+                    and "SMEAGOL_B200_TC_KIND" not in os.environ):
+                info = (ctypes.c_int64 * 4)()
+                _lib.check(self.lib.smg_seed_prepare(pwmset.handle, int(wk), info), "smg_seed_prepare")
+                if info[3] == 1 and info[0] > 0:
+                    self.seed_len, self.seed_nv, self._seed_hl = int(wk), int(info[0]), int(info[1])
+                    self.tc_kind = "seed"
         self.pwmset, self.batch = pwmset, batch
         dev = batch.device
         M = pwmset.n_motifs
@@ -371,9 +383,33 @@ class ScanPlan:
                 raise ValueError("candidate key does not fit in 62 bits")
             # tc5: every epilogue warp of every CTA keeps two blocks of 128 candidate slots reserved
             self.cand_cap = int(self.hit_cap * 1.25) + 4096 + ((1 << 20) if self.tc_kind == "tc5" else 0)
+            if self.tc_kind == "seed":  # ~0.1 (12-mer seeds) .. 0.5 (10-mers) candidates per position and strand
+                per = {12: 0.15, 11: 0.35}.get(self.seed_len, 0.7)
+                self.cand_cap = int(batch.total_own * 2 * per) + (1 << 16)
         self._alloc()
         if self.kmer_w > 0:
             self._build_kmer_index()
+        if self.seed_len > 0:
+            self._build_seed_index()
+
+    def _build_seed_index(self):
+        """One-class k-mer index of the wide PWMs' seeds for this plan's thresholds (csrc/kmer.h: seed engine)."""
+        dev, lib = self.batch.device, self.lib
+        self.seed_head = torch.empty(max(self._seed_hl, 1), dtype=torch.int32, device=dev)
+        cap = max(1 << 16, min(int(4.0 ** self.seed_len * 0.15), 1 << 27))
+        ctr = torch.zeros(_lib.N_COUNTERS, dtype=torch.int64, device=dev)
+        while True:
+            self.seed_entries = torch.empty(cap * 16, dtype=torch.uint8, device=dev)
+            ctr.zero_()
+            _lib.check(lib.smg_seed_index_build(self.pwmset.handle, self.seed_len, self.strands, _ptr(self.d_lo), _ptr(self.seed_head),
+                                                self._seed_hl, _ptr(self.seed_entries), cap, _ptr(ctr), _stream()), "smg_seed_index_build")
+            need = int(ctr[_lib.CTR_KMER_ENTRIES].item())
+            if need <= cap:
+                break
+            if need >= (1 << 31) - 1:
+                raise _lib.SmeagolB200Error("seed index too large (threshold too low for the seed engine)")
+            cap = min(int(need * 1.1) + 1024, (1 << 31) - 2)
+        self.seed_cap, self.seed_n_entries, self._seed_ctr = cap, need, ctr
 
     def _build_kmer_index(self):
         """Score every k-mer of the narrow width classes once for this plan's thresholds (csrc/kmer.cu)."""
@@ -403,6 +439,11 @@ class ScanPlan:
     def launch_kmer_build(self):
         """Enqueue the k-mer index build again (same thresholds, known capacity, no host sync): what a fresh call pays
         per (PWM set, thresholds) -- benchmarks put it inside the timed step."""
+        if self.seed_len > 0:
+            self._seed_ctr.zero_()
+            _lib.check(self.lib.smg_seed_index_build(self.pwmset.handle, self.seed_len, self.strands, _ptr(self.d_lo),
+                                                     _ptr(self.seed_head), self._seed_hl, _ptr(self.seed_entries), self.seed_cap,
+                                                     _ptr(self._seed_ctr), _stream()), "smg_seed_index_build")
         if self.kmer_w <= 0:
             return
         self._kmer_ctr.zero_()
@@ -461,6 +502,14 @@ class ScanPlan:
     def launch_tc_side(self):
         """Tensor-core prefilter + exact second pass on its side of the width split."""
         b, lib = self.batch, self.lib
+        if self.tc_kind == "seed":
+            _lib.check(lib.smg_scan_seed(self.pwmset.handle, self.seed_len, _ptr(b.packed), _ptr(b.amask), _ptr(b.codes), _ptr(b.d_rows),
+                                         b.n_rows, _ptr(self.d_out_rows), _ptr(self.d_chunks), self.n_chunks, self.chunk_len,
+                                         self.strands, _ptr(self.d_lo), _ptr(self.d_hi), _ptr(self.d_thr), self.pos_bits,
+                                         self.motif_bits, self.cand_pos_bits, _ptr(self.seed_head), _ptr(self.seed_entries),
+                                         _ptr(self.cand), self.cand_cap, _ptr(self.keys), _ptr(self.scores), self.hit_cap,
+                                         _ptr(self.counts), _ptr(self.counters), _stream()), "smg_scan_seed")
+            return
         fn = lib.smg_scan_tc5 if self.tc_kind == "tc5" else lib.smg_scan_tc
         _lib.check(fn(self.pwmset.handle, _ptr(b.packed), _ptr(b.amask), _ptr(b.codes), _ptr(b.d_rows), b.n_rows,
                                    _ptr(self.d_out_rows), _ptr(self.d_chunks), self.n_chunks, self.chunk_len, self.strands,

@@ -553,6 +553,8 @@ def test_kmer_index_engine_bit_identical(monkeypatch):
         model = sb.models.PWMModel(df)  # default split: engine 'auto' = k-mer index + register tables + tensor cores
         res, exp = check_against_oracle(model, seqs, 0.6, "both", chunk_len=512)
         assert res.stats["engine"] == "auto" and res.stats["kmer_max_width"] == int(wk)
+        # a 12-mer index also carries the SEEDS of the wider PWMs (W 13, 14 here) instead of the tensor-core prefilter
+        assert res.stats["tc_kind"] == ("seed" if wk == "12" else "tc5")
         assert res.stats["kmer_index_entries"] > 0
         check_against_oracle(model, seqs, 0.6, "none")
         check_against_oracle(model, seqs, 0.6, "only", chunk_len=4096)
