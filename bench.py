@@ -255,6 +255,23 @@ def tensor_side_roofline(dset, total_bases, tc_ms, step_ms, peaks, peaks_kind, t
                 "sustained" if "bf16_tflops_sustained" in peaks else "burst", peaks_kind)}
 
 
+def index_scan_roofline(total_bases, n_hits, scan_ms, step_ms, peaks, peaks_kind, traffic, kmer_w, n_pwms):
+    """Roofline of smg::scan_kmer_kernel, the dominant kernel when both sides of the width split run on per-call k-mer
+    indexes.  The kernel does no per-cell arithmetic: it is OUTPUT-bound -- per launch it must read
+    the packed sequence (2 bits + 1 mask bit per base) and write 12 bytes per hit (64-bit key + fp32 score)."""
+    alg_bytes = total_bases * 0.375 + n_hits * 12.0
+    peak = float(peaks.get("hbm_gbs_sustained", peaks.get("hbm_gbs", 6459.0)))
+    t = scan_ms * 1e-3
+    return {"bound": "hbm", "achieved": alg_bytes / t / 1e9, "peak": peak, "unit": "GB/s", "frac": alg_bytes / t / 1e9 / peak,
+            "traffic": traffic,
+            "kernel": "smg::scan_kmer_kernel: %d PWMs of width <= %d through the per-call k-mer index" % (n_pwms, kmer_w),
+            "kernel_ms": scan_ms, "kernel_share_of_step": scan_ms / step_ms,
+            "algorithmic": "bytes per launch = 0.375 B per base (2-bit codes + ambiguity mask) + 12 B per emitted hit (%d hits); "
+                           "the kernel is bound by dependent L2 look-ups (bitmap -> list head -> entry) and the hit write-out, "
+                           "not by arithmetic: see fp32_pipe_view for the rate in SURVEY 8(d)'s lookup-add units" % n_hits,
+            "peak_source": "MEASURED_PEAKS.json HBM copy bandwidth (%s)" % peaks_kind}
+
+
 # ------------------------------------------------------------------------------------------------ c4 (headline)
 def run_c4(args, rank, world, local_rank, device, peaks, peaks_kind, warmup):
     import torch
@@ -279,6 +296,12 @@ def run_c4(args, rank, world, local_rank, device, peaks, peaks_kind, warmup):
     res0 = plan.finish(sort=False)  # calibrates the hit buffer; the workload is deterministic
     n_hits = res0.n_hits
     batch_own = batch.total_own
+    n_kmer_hits = 0
+    if plan.engine == "auto" and plan.kmer_w > 0:  # hits written by the k-mer scan alone (its algorithmic output bytes)
+        plan.counters.zero_()
+        plan.counts.zero_()
+        plan.launch_kmer_side()
+        n_kmer_hits = int(plan.counters.cpu().numpy()[_lib.CTR_HITS_APPENDED])
     keys_out = torch.empty(max(n_hits, 1), dtype=torch.int64, device=device)
     scores_out = torch.empty(max(n_hits, 1), dtype=torch.float32, device=device)
     sort_tmp = torch.empty(16, dtype=torch.uint8, device=device)
@@ -291,7 +314,9 @@ def run_c4(args, rank, world, local_rank, device, peaks, peaks_kind, warmup):
         plan.counters.zero_()
         plan.counts.zero_()
         if plan.engine == "auto":
-            plan.launch_kmer_build()  # per-call index of (PWM set, thresholds): inside the step
+            plan.launch_kmer_build()  # per-call indexes of (PWM set, thresholds): inside the step
+            if ev:
+                ev[6].record()
             plan.launch_kmer_side()
             if ev:
                 ev[5].record()
@@ -304,6 +329,7 @@ def run_c4(args, rank, world, local_rank, device, peaks, peaks_kind, warmup):
         else:
             plan.launch()
             if ev:
+                ev[6].record()
                 ev[5].record()
                 ev[1].record()
                 ev[2].record()
@@ -326,7 +352,7 @@ def run_c4(args, rank, world, local_rank, device, peaks, peaks_kind, warmup):
     if world > 1:
         dist.barrier()
     sampler.t_start = time.perf_counter()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(7)] for _ in range(args.steps)]
     launches0 = _lib.launch_count()
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
@@ -338,6 +364,8 @@ def run_c4(args, rank, world, local_rank, device, peaks, peaks_kind, warmup):
     launches = _lib.launch_count() - launches0
     step_ms = float(np.mean([e[0].elapsed_time(e[4]) for e in evs]))
     kmer_ms = float(np.mean([e[0].elapsed_time(e[5]) for e in evs]))
+    build_ms = float(np.mean([e[0].elapsed_time(e[6]) for e in evs]))
+    kmer_scan_ms = kmer_ms - build_ms
     regtab_ms = float(np.mean([e[5].elapsed_time(e[1]) for e in evs]))
     tc_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
     sort_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
@@ -362,6 +390,8 @@ def run_c4(args, rank, world, local_rank, device, peaks, peaks_kind, warmup):
     counts_host = torch.empty((1, M, 2), dtype=torch.int32, pin_memory=True)
     h2d = int(batch.h2d_bytes + batch.n_rows * 40)
     plan_hit_cap = plan.hit_cap
+    plan_kmer_w = plan.kmer_w
+    plan_n_kmer_pwms = int((dset.widths <= plan.kmer_w).sum())
     del plan, batch
     torch.cuda.empty_cache()
     n_e2e = max(1, min(args.steps, 3))
@@ -392,10 +422,16 @@ def run_c4(args, rank, world, local_rank, device, peaks, peaks_kind, warmup):
         traffic = load_traffic("c4_n1_dominant_kernel_dram_bytes") if (world == 1 and args.scale == 1.0) else None
         sort_bytes = load_traffic("c4_n1_sort_dram_bytes") if (world == 1 and args.scale == 1.0) else None
         my_bases = L // world
-        roofline = tensor_side_roofline(dset, my_bases, tc_ms, step_ms, peaks, peaks_kind, tc_kind, traffic)
+        if tc_kind == "seed":
+            roofline = index_scan_roofline(my_bases, n_kmer_hits, kmer_scan_ms, step_ms, peaks, peaks_kind,
+                                           load_traffic("c4_n1_kmer_scan_dram_bytes") if (world == 1 and args.scale == 1.0) else None,
+                                           plan_kmer_w, plan_n_kmer_pwms)
+        else:
+            roofline = tensor_side_roofline(dset, my_bases, tc_ms, step_ms, peaks, peaks_kind, tc_kind, traffic)
         w = dset.widths.astype(np.int64)
         lookups = my_bases * 2 * int(w.sum())
-        roofline["step_breakdown_ms"] = {"kmer_index_side": kmer_ms, "register_table_side": regtab_ms, "tensor_core_side": tc_ms,
+        roofline["step_breakdown_ms"] = {"index_builds": build_ms, "kmer_scan": kmer_scan_ms, "register_table_side": regtab_ms,
+                                         ("seed_side" if tc_kind == "seed" else "tensor_core_side"): tc_ms,
                                          "sort": sort_ms, "count_sum_allreduce": coll_ms}
         roofline["sort_dram_bytes"] = sort_bytes
         roofline["algorithmic_dram_bytes"] = int(my_bases * 0.375 + n_hits * 12 + M * 8)
@@ -530,7 +566,8 @@ def run_c2(args, rank, world, local_rank, device, peaks, peaks_kind, warmup, ste
     e2e_t = allreduce_max(float(np.mean(e2e_times)), world, device)
     out = {"workload": C2_WORKLOAD, "value": value, "unit": "Gbase*motif/s", "ms_per_step": ms_per_step, "steps": steps,
            "scaling": "weak", "n_hits_per_gpu": n_hits, "hit_density": n_hits / (2.0 * units), "gpu_launches": int(launches),
-           "step_breakdown_ms": {"kmer_index_and_register_table_side": regtab_ms, "tensor_core_side": tc_ms,
+           "step_breakdown_ms": {"index_builds_kmer_scan_and_register_table_side": regtab_ms,
+                                 ("seed_side" if stats.get("tc_kind") == "seed" else "tensor_core_side"): tc_ms,
                                  "sort_and_collective": sort_ms},
            "engine": stats.get("engine"), "tc_kind": stats.get("tc_kind"), "kmer_max_width": stats.get("kmer_max_width"),
            "e2e_device_api": {"value": units * world / e2e_t / 1e9, "ms_per_step": e2e_t * 1e3,
@@ -538,8 +575,15 @@ def run_c2(args, rank, world, local_rank, device, peaks, peaks_kind, warmup, ste
                               "d2h_bytes_per_step": int(plan.counts.numel() * 4 + 64),
                               "note": "H2D ASCII genomes (pinned) + pack + scan + sort + D2H count table; site list stays on device"}}
     if rank == 0:
-        out["roofline"] = tensor_side_roofline(pset, total_bases, tc_ms, step_ms, peaks, peaks_kind, stats.get("tc_kind") or "hmma",
-                                               load_traffic("c2_dominant_kernel_dram_bytes"))
+        if stats.get("tc_kind") == "seed":
+            # index builds + k-mer scan are timed together here (no event between them); hits of the narrow PWMs ~ all hits
+            out["roofline"] = index_scan_roofline(total_bases, n_hits, regtab_ms, step_ms, peaks, peaks_kind,
+                                                  load_traffic("c2_kmer_scan_dram_bytes"), int(stats.get("kmer_max_width") or 0),
+                                                  int((pset.widths <= int(stats.get("kmer_max_width") or 0)).sum()))
+            out["roofline"]["note"] = "kernel_ms here includes the per-call index builds of both engines"
+        else:
+            out["roofline"] = tensor_side_roofline(pset, total_bases, tc_ms, step_ms, peaks, peaks_kind,
+                                                   stats.get("tc_kind") or "hmma", load_traffic("c2_dominant_kernel_dram_bytes"))
     if with_frames and rank == 0:
         # the PUBLIC call, like for like with the reference arm: records in, `counts` (and `sites`) DataFrames out
         import smeagol_b200 as sb
