@@ -284,7 +284,7 @@ int smg_variant_windows_mode(smg_pwmset_t set, const uint32_t* d_packed, const u
  * threshold - (maximum of the remaining positions); every (PWM, strand) becomes a forward-only virtual PWM of width
  * seed_len in a one-class k-mer index built per call, and the scan turns every list entry into a candidate window that
  * finalize re-scores.  smg_seed_prepare: info[0] = virtual PWMs, info[1] = int32 slots of the index buffer (d_head),
- * info[2] = largest seed offset, info[3] = 1 if every PWM of the tensor-core side is seedable (W <= seed_len + 12). */
+ * info[2] = largest seed offset, info[3] = 1 if every PWM of the tensor-core side is seedable (W <= seed_len + 14). */
 int smg_seed_prepare(smg_pwmset_t set, int seed_len, int64_t info[4]);
 int smg_seed_index_build(smg_pwmset_t set, int seed_len, int strands, const float* d_thr_lo, int32_t* d_head, int64_t head_len,
                          smg_kmer_entry_t* d_entries, uint64_t entry_cap, uint64_t* d_counters, void* stream);

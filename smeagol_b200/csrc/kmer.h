@@ -43,7 +43,7 @@ struct KmerParams {
 // ---- seed engine (wide PWMs through the k-mer machinery): a window of a PWM of width W > S can only be a hit if its
 // most selective S consecutive positions (the SEED, at offset o of the window) score more than thr - (maximum of the
 // rest); every (PWM, strand) becomes a VIRTUAL forward-only PWM of width S in a one-class k-mer index built per call.
-constexpr int kSeedMaxRest = 12;  // a PWM is seeded when W <= S + kSeedMaxRest
+constexpr int kSeedMaxRest = 14;  // a PWM is seeded when W <= S + kSeedMaxRest
 struct SeedParams {
     ScanParams sp;                 // the REAL PWM set (rows, chunks, candidate key layout)
     const int32_t* head;           // one-class index of the virtual PWMs

@@ -20,7 +20,8 @@ NEAR_REL = 1e-5     # half-width of the near-threshold band, relative to sum_k m
 STRANDS = {"none": 1, "only": 2, "both": 3}
 DEFAULT_ENGINE = "regtab"
 DEFAULT_TC_KIND = "tc5"
-SEED_MIN_LEN = 10     # the seed engine replaces the tensor-core prefilter when the k-mer index reaches this width
+SEED_MIN_LEN = 11     # shortest seed of the seed engine (csrc/kmer.h); 12 is the longest the index supports
+SEED_MAX_REST = 14    # a PWM is seeded when W <= seed length + this
 KMER_MAX_WIDTH = 12   # widest class of the k-mer index engine (csrc/kmer.cu)
 KMER_ALPHA = 1.5     # a width class joins the k-mer index when 4^W <= KMER_ALPHA * window starts (break-even of index build vs tcgen05 scan, profiles/r02_bench_widths.txt)
                       # k-mers once costs about as much per (k-mer, PWM) as any engine spends per (position, PWM)  # tensor-core prefilter of the 'auto' / tensor-core engines: 'hmma' (mma.sync) or 'tc5' (tcgen05 + TMEM)
@@ -329,13 +330,30 @@ class ScanPlan:
             # ---- seed engine: when the scan is long enough for a 10..12-mer index, the wide PWMs go through it too
             # (seed = their most selective kmer_w positions, csrc/kmer.h) instead of the tensor-core prefilter
             self.seed_len = 0
-            if (wk >= SEED_MIN_LEN and self.kmer_w > 0 and os.environ.get("SMEAGOL_B200_SEED", "1") != "0"
+            if (wk >= SEED_MIN_LEN and os.environ.get("SMEAGOL_B200_SEED", "1") != "0"
                     and "SMEAGOL_B200_TC_KIND" not in os.environ):
-                info = (ctypes.c_int64 * 4)()
-                _lib.check(self.lib.smg_seed_prepare(pwmset.handle, int(wk), info), "smg_seed_prepare")
-                if info[3] == 1 and info[0] > 0:
-                    self.seed_len, self.seed_nv, self._seed_hl = int(wk), int(info[0]), int(info[1])
-                    self.tc_kind = "seed"
+                # cost model from profiles/r02_bench_widths.txt and the c4 / c2 steps: the per-call seed index costs
+                # ~1.4e-13 s per (S-mer, column), its scan + exact pass ~1.6e-11 s per position (more with shorter seeds);
+                # the tcgen05 prefilter ~1.2e-13 s per (position, column).  Seeds win on long scans, lose on short ones.
+                wt = pwmset.widths
+                tc_w = wt[(wt > max(self.kmer_w, pwmset.tc_min_width - 1)) & (wt <= 32)]
+                nv, L = 2 * int(tc_w.size), float(max(batch.total_own, 1))
+                best = None
+                for S in range(min(wk, KMER_MAX_WIDTH), SEED_MIN_LEN - 1, -1):
+                    if nv == 0 or int(tc_w.min()) <= S or int(tc_w.max()) > S + SEED_MAX_REST:
+                        continue
+                    cost = nv * 4.0 ** S * 1.4e-13 + L * 1.6e-11 * (1.0 + 0.3 * (KMER_MAX_WIDTH - S))
+                    if best is None or cost < best[0]:
+                        best = (cost, S)
+                forced = os.environ.get("SMEAGOL_B200_SEED_LEN")
+                if forced is not None and nv:
+                    best = (0.0, int(forced))
+                if best is not None and best[0] < L * nv * 1.2e-13:
+                    info = (ctypes.c_int64 * 4)()
+                    _lib.check(self.lib.smg_seed_prepare(pwmset.handle, best[1], info), "smg_seed_prepare")
+                    if info[3] == 1 and info[0] > 0:
+                        self.seed_len, self.seed_nv, self._seed_hl = best[1], int(info[0]), int(info[1])
+                        self.tc_kind = "seed"
         self.pwmset, self.batch = pwmset, batch
         dev = batch.device
         M = pwmset.n_motifs

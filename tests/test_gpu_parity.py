@@ -548,16 +548,22 @@ def test_kmer_index_engine_bit_identical(monkeypatch):
     pa = np.array([0.23] * 4 + [0.08 / 12] * 12)
     seqs = [rand_seq(rng, 6000), rand_seq(rng, 1500, amb, pa / pa.sum()), rand_seq(rng, 31), "ACGTA", "",
             "N" * 40 + rand_seq(rng, 300) + "N" * 40]
-    for wk in ("12", "7", "3"):
+    for wk in ("12", "11", "7", "3"):
         monkeypatch.setenv("SMEAGOL_B200_KMER_MAX_WIDTH", wk)
+        # the seed engine is chosen by a cost model (long scans only): force it here, with 12- and 11-base seeds
+        if wk in ("12", "11"):
+            monkeypatch.setenv("SMEAGOL_B200_SEED_LEN", wk)
+        else:
+            monkeypatch.delenv("SMEAGOL_B200_SEED_LEN", raising=False)
         model = sb.models.PWMModel(df)  # default split: engine 'auto' = k-mer index + register tables + tensor cores
         res, exp = check_against_oracle(model, seqs, 0.6, "both", chunk_len=512)
         assert res.stats["engine"] == "auto" and res.stats["kmer_max_width"] == int(wk)
         # a 12-mer index also carries the SEEDS of the wider PWMs (W 13, 14 here) instead of the tensor-core prefilter
-        assert res.stats["tc_kind"] == ("seed" if wk == "12" else "tc5")
+        assert res.stats["tc_kind"] == ("seed" if wk in ("12", "11") else "tc5")
         assert res.stats["kmer_index_entries"] > 0
         check_against_oracle(model, seqs, 0.6, "none")
         check_against_oracle(model, seqs, 0.6, "only", chunk_len=4096)
+    monkeypatch.delenv("SMEAGOL_B200_SEED_LEN", raising=False)
     monkeypatch.setenv("SMEAGOL_B200_KMER_MAX_WIDTH", "10")
     model = sb.models.PWMModel(df)
     check_against_oracle(model, seqs, 1.0, "both")
