@@ -334,7 +334,7 @@ class ScanPlan:
                     and "SMEAGOL_B200_TC_KIND" not in os.environ):
                 # cost model from profiles/r02_bench_widths.txt and the c4 / c2 steps: the per-call seed index costs
                 # ~1.4e-13 s per (S-mer, column), its scan + exact pass ~1.6e-11 s per position (more with shorter seeds);
-                # the tcgen05 prefilter ~1.2e-13 s per (position, column).  Seeds win on long scans, lose on short ones.
+                # the tcgen05 prefilter 1.1 .. 1.7e-13 s per (position, column).  Seeds win on long scans, lose on short ones.
                 wt = pwmset.widths
                 tc_w = wt[(wt > max(self.kmer_w, pwmset.tc_min_width - 1)) & (wt <= 32)]
                 nv, L = 2 * int(tc_w.size), float(max(batch.total_own, 1))
@@ -348,7 +348,7 @@ class ScanPlan:
                 forced = os.environ.get("SMEAGOL_B200_SEED_LEN")
                 if forced is not None and nv:
                     best = (0.0, int(forced))
-                if best is not None and best[0] < L * nv * 1.2e-13:
+                if best is not None and best[0] < L * nv * 1.4e-13:
                     info = (ctypes.c_int64 * 4)()
                     _lib.check(self.lib.smg_seed_prepare(pwmset.handle, best[1], info), "smg_seed_prepare")
                     if info[3] == 1 and info[0] > 0:
