@@ -333,7 +333,8 @@ class ScanPlan:
             if (wk >= SEED_MIN_LEN and os.environ.get("SMEAGOL_B200_SEED", "1") != "0"
                     and "SMEAGOL_B200_TC_KIND" not in os.environ):
                 # cost model from profiles/r02_bench_widths.txt and the c4 / c2 steps: the per-call seed index costs
-                # ~1.4e-13 s per (S-mer, column), its scan + exact pass ~1.6e-11 s per position (more with shorter seeds);
+                # ~1.4e-13 s per (S-mer, column), its scan + exact pass 0.8e-11 s per position + 1.2e-14 s per (position,
+                # column) with 12-base seeds, twice that with 11 (candidates double per base the seed loses);
                 # the tcgen05 prefilter 1.1 .. 1.7e-13 s per (position, column).  Seeds win on long scans, lose on short ones.
                 wt = pwmset.widths
                 tc_w = wt[(wt > max(self.kmer_w, pwmset.tc_min_width - 1)) & (wt <= 32)]
@@ -342,7 +343,7 @@ class ScanPlan:
                 for S in range(min(wk, KMER_MAX_WIDTH), SEED_MIN_LEN - 1, -1):
                     if nv == 0 or int(tc_w.min()) <= S or int(tc_w.max()) > S + SEED_MAX_REST:
                         continue
-                    cost = nv * 4.0 ** S * 1.4e-13 + L * 1.6e-11 * (1.0 + 0.3 * (KMER_MAX_WIDTH - S))
+                    cost = nv * 4.0 ** S * 1.4e-13 + L * (0.8e-11 + nv * 1.2e-14 * 2.0 ** (KMER_MAX_WIDTH - S))
                     if best is None or cost < best[0]:
                         best = (cost, S)
                 forced = os.environ.get("SMEAGOL_B200_SEED_LEN")
