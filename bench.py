@@ -13,15 +13,19 @@ the single exchange is one NCCL all_reduce of the (1, M, 2) count table per step
 alone (weak scaling: one shard per rank).
 
 Timed regions
-  value : the rank's packed range already resident in HBM; per step = reset counters/counts, fused scan (both
-          engines), fp64 adjudication, sort of the rank's hit list into the reference's (row, pos, motif) order, sum of
-          the per-segment count tables and the all_reduce.  CUDA events per step on the launching stream; the working
+  value : the rank's packed range already resident in HBM; per step = reset counters/counts, the per-call index builds
+          (k-mer index of the narrow PWMs, seed index of the wide ones), k-mer scan, seed scan + exact second pass (or
+          the tcgen05 prefilter + second pass where the seed engine does not apply), fp64 adjudication, sort of the
+          rank's hit list into the reference's (row, pos, motif) order, sum of the per-segment count tables and the
+          all_reduce.  CUDA events per step on the launching stream; the working
           set (93 MB packed sequence + > 4 GB of hits at N=1) is larger than L2; max over ranks.
   e2e   : the same work through the public multi-GPU seam dist.scan_long_sequence() from a pinned HOST buffer: H2D
           of the rank's range, 2-bit pack kernel, scan, sort, all_reduce, then D2H of the count table and the hit
           counters.  The sorted site list stays on the device (3.9 GB at N=1: no reference-style DataFrame of 3e8
           rows exists on any host); wall clock around synchronised steps.
-  roofline : the dominant kernel of the step, timed live with CUDA events around its C-ABI call.
+  roofline : the dominant kernel of the step, timed live with CUDA events around its C-ABI call: the k-mer scan
+          (output-bound, against the HBM copy bandwidth) when both sides run on per-call indexes, else the tensor side
+          (against the sustained bf16 peak); the step breakdown and SURVEY 8(d)'s lookup-add rate ride along.
   cpu_baseline / --impl reference : the reference pipeline's CPU port (oracle/ref_port.py: per-base Python encoding,
           dense conv, np.where, pandas) with all host threads on BASELINE.md section 3's c4 recipe: 100 kb chunks
           with a (W_max - 1)-base halo from a 5 Mb slice of the same chromosome (the reference cannot run c4 unchunked:
