@@ -288,6 +288,44 @@ def pick_chunk_len(total_own, n_groups, target_ctas=148 * 16 * 8, n_rows=1):
     return int(min(cap, max(256, c)))
 
 
+def choose_index_engines(widths, tc_min_width, total_own, forced_kmer=None, forced_seed=None, allow_seed=True):
+    """Which per-call indexes a scan of `total_own` window starts uses (host logic, no GPU): returns (wk, kmer_w, seed_len).
+
+    wk: widest class the k-mer index may take, 4^W <= KMER_ALPHA * window starts (the measured break-even of the index
+    build against the tcgen05 scan, profiles/r02_bench_widths.txt); kmer_w: widest PRESENT width <= wk (0: no k-mer
+    side).  seed_len: 0, or the seed length (11 / 12) when the seed engine is cheaper than the tensor-core prefilter for
+    the PWMs on the tensor-core side.  Cost model from the c4 / c2 steps and the per-width matrix: the per-call seed
+    index costs ~1.4e-13 s per (S-mer, column); its scan + exact pass 0.8e-11 s per position + 1.2e-14 s per (position,
+    column) with 12-base seeds, twice that with 11 (candidates double per base the seed loses); the tcgen05 prefilter
+    1.1 .. 1.7e-13 s per (position, column).  Seeds win on long scans and lose on short ones."""
+    widths = np.asarray(widths)
+    wk = 0
+    for w in range(1, KMER_MAX_WIDTH + 1):
+        if 4 ** w <= KMER_ALPHA * max(total_own, 1):
+            wk = w
+    if forced_kmer is not None:
+        wk = max(0, min(KMER_MAX_WIDTH, int(forced_kmer)))
+    present = np.unique(widths)
+    present = present[present <= wk]
+    kmer_w = int(present.max()) if present.size else 0
+    seed_len = 0
+    if allow_seed and wk >= SEED_MIN_LEN:
+        tc_w = widths[(widths > max(kmer_w, tc_min_width - 1)) & (widths <= 32)]
+        nv, L = 2 * int(tc_w.size), float(max(total_own, 1))
+        best = None
+        for S in range(min(wk, KMER_MAX_WIDTH), SEED_MIN_LEN - 1, -1):
+            if nv == 0 or int(tc_w.min()) <= S or int(tc_w.max()) > S + SEED_MAX_REST:
+                continue
+            cost = nv * 4.0 ** S * 1.4e-13 + L * (0.8e-11 + nv * 1.2e-14 * 2.0 ** (KMER_MAX_WIDTH - S))
+            if best is None or cost < best[0]:
+                best = (cost, S)
+        if forced_seed is not None and nv:
+            best = (0.0, int(forced_seed))
+        if best is not None and best[0] < L * nv * 1.4e-13:
+            seed_len = best[1]
+    return wk, kmer_w, seed_len
+
+
 class ScanPlan:
     """A prepared fused scan: all device buffers allocated once, kernels enqueued without host synchronisation.
 
@@ -316,45 +354,17 @@ class ScanPlan:
         self.kmer_w = 0
         self.seed_len = 0
         if self.engine == "auto" and os.environ.get("SMEAGOL_B200_KMER", "1") != "0":
-            forced = os.environ.get("SMEAGOL_B200_KMER_MAX_WIDTH")
-            wk = 0
-            for w in range(1, KMER_MAX_WIDTH + 1):
-                if 4 ** w <= KMER_ALPHA * max(batch.total_own, 1):
-                    wk = w
-            if forced is not None:
-                wk = max(0, min(KMER_MAX_WIDTH, int(forced)))
-            present = np.unique(pwmset.widths)
-            present = present[present <= wk]
-            self.kmer_w = int(present.max()) if present.size else 0
+            wk, self.kmer_w, want_seed = choose_index_engines(
+                pwmset.widths, pwmset.tc_min_width, batch.total_own, os.environ.get("SMEAGOL_B200_KMER_MAX_WIDTH"),
+                os.environ.get("SMEAGOL_B200_SEED_LEN"),
+                os.environ.get("SMEAGOL_B200_SEED", "1") != "0" and "SMEAGOL_B200_TC_KIND" not in os.environ)
             pwmset = pwmset.with_kmer(self.kmer_w)
-            # ---- seed engine: when the scan is long enough for a 10..12-mer index, the wide PWMs go through it too
-            # (seed = their most selective kmer_w positions, csrc/kmer.h) instead of the tensor-core prefilter
-            self.seed_len = 0
-            if (wk >= SEED_MIN_LEN and os.environ.get("SMEAGOL_B200_SEED", "1") != "0"
-                    and "SMEAGOL_B200_TC_KIND" not in os.environ):
-                # cost model from profiles/r02_bench_widths.txt and the c4 / c2 steps: the per-call seed index costs
-                # ~1.4e-13 s per (S-mer, column), its scan + exact pass 0.8e-11 s per position + 1.2e-14 s per (position,
-                # column) with 12-base seeds, twice that with 11 (candidates double per base the seed loses);
-                # the tcgen05 prefilter 1.1 .. 1.7e-13 s per (position, column).  Seeds win on long scans, lose on short ones.
-                wt = pwmset.widths
-                tc_w = wt[(wt > max(self.kmer_w, pwmset.tc_min_width - 1)) & (wt <= 32)]
-                nv, L = 2 * int(tc_w.size), float(max(batch.total_own, 1))
-                best = None
-                for S in range(min(wk, KMER_MAX_WIDTH), SEED_MIN_LEN - 1, -1):
-                    if nv == 0 or int(tc_w.min()) <= S or int(tc_w.max()) > S + SEED_MAX_REST:
-                        continue
-                    cost = nv * 4.0 ** S * 1.4e-13 + L * (0.8e-11 + nv * 1.2e-14 * 2.0 ** (KMER_MAX_WIDTH - S))
-                    if best is None or cost < best[0]:
-                        best = (cost, S)
-                forced = os.environ.get("SMEAGOL_B200_SEED_LEN")
-                if forced is not None and nv:
-                    best = (0.0, int(forced))
-                if best is not None and best[0] < L * nv * 1.4e-13:
-                    info = (ctypes.c_int64 * 4)()
-                    _lib.check(self.lib.smg_seed_prepare(pwmset.handle, best[1], info), "smg_seed_prepare")
-                    if info[3] == 1 and info[0] > 0:
-                        self.seed_len, self.seed_nv, self._seed_hl = best[1], int(info[0]), int(info[1])
-                        self.tc_kind = "seed"
+            if want_seed:
+                info = (ctypes.c_int64 * 4)()
+                _lib.check(self.lib.smg_seed_prepare(pwmset.handle, want_seed, info), "smg_seed_prepare")
+                if info[3] == 1 and info[0] > 0:
+                    self.seed_len, self.seed_nv, self._seed_hl = want_seed, int(info[0]), int(info[1])
+                    self.tc_kind = "seed"
         self.pwmset, self.batch = pwmset, batch
         dev = batch.device
         M = pwmset.n_motifs

@@ -347,3 +347,22 @@ def test_window_and_similarity_host_functions_replay_the_reference():
             np.testing.assert_allclose(enr[c].astype(float), np.array(exp[c], dtype=float), rtol=1e-9, atol=1e-12, err_msg=c)
         one = sb.enrich.enrich_in_window(w.iloc[1], sites, genome, matrix_id=Wd["matrix_id"])
         assert one["count"] == exp["count"][1] and abs(float(one["p"]) - exp["p"][1]) < 1e-12
+
+
+def test_choice_of_the_per_call_index_engines():
+    """device.choose_index_engines (host logic of ScanPlan): which width classes the k-mer index takes (4^W against the
+    scan length) and whether the wide PWMs go through the seed engine or the tensor-core prefilter (cost model)."""
+    from smeagol_b200 import synth
+
+    w4 = np.array(synth.jaspar_widths(1000))                     # c4: W 6..24
+    assert dev.choose_index_engines(w4, 7, 248_000_000) == (12, 12, 12)          # whole chromosome on one GPU: 12-base seeds
+    wk, kw, sl = dev.choose_index_engines(w4, 7, 31_000_000)                     # one eighth of it: a cheaper 11-base seed index
+    assert (wk, kw) == (12, 12) and sl in (11, 12)
+    assert dev.choose_index_engines(w4, 7, 30_000) == (7, 7, 0)                  # short scan: no seeds, classes up to 4^7 <= 45,000
+    w2 = np.array([7, 8, 9, 10, 11, 12] * 100)                                   # c2-like: W 7..12, 10 Mb
+    assert dev.choose_index_engines(w2, 7, 10_000_000) == (11, 11, 11)           # W=12 PWMs seeded with 11-mers
+    assert dev.choose_index_engines(np.full(1024, 16), 7, 4_000_000)[2] == 0     # 4 Mb x 1,024 wide PWMs: the prefilter is cheaper
+    assert dev.choose_index_engines(np.full(8, 30), 7, 248_000_000)[2] == 0      # W = 30 > seed + 14: not seedable
+    assert dev.choose_index_engines(w4, 7, 248_000_000, allow_seed=False)[2] == 0
+    assert dev.choose_index_engines(w4, 7, 1000, forced_kmer="12", forced_seed="12") == (12, 12, 12)  # test switches
+    assert dev.choose_index_engines(w4, 7, 248_000_000, forced_kmer="0") == (0, 0, 0)
