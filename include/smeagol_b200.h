@@ -68,7 +68,7 @@ typedef struct {
 #define SMG_CTR_CANDIDATES 5    /* smg_scan_tc: candidates emitted by the tensor-core prefilter (> cand_cap: overflow) */
 #define SMG_CTR_NEAR_TC 6       /* smg_scan_tc: near-threshold candidates adjudicated inside its exact pass (a tally: they
                                    never occupy d_near, so they do not count against near_cap) */
-#define SMG_CTR_KMER_ENTRIES 7   /* smg_kmer_index_build: entries written (> entry_cap: overflow, rebuild with a larger buffer) */
+#define SMG_CTR_KMER_ENTRIES 7   /* smg_kmer_index_build / smg_seed_index_build: entry slots reserved, in blocks of 64 per warp (> entry_cap: overflow, rebuild with a larger buffer) */
 #define SMG_N_COUNTERS 8
 
 /* one (k-mer, PWM, strand) hit of the k-mer index: col = motif * 2 + strand | flags (bit 30: decided by the fp64

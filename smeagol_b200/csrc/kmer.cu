@@ -15,6 +15,10 @@
 //   scan    one thread = one window start; a CTA stages its hits in shared memory and appends them to the global hit list
 //           with one atomic per flush; per-(motif, strand) counts in a shared-memory histogram, flushed per chunk
 //   windows that contain an IUPAC code, 'Z' or the end of the row are scored directly (rare generic path).
+//
+// SEED ENGINE (smg_seed_index_build / smg_scan_seed, at the end of this file): the same index machinery for the WIDE
+// PWMs -- each (PWM, strand) enters a one-class index as a forward-only virtual PWM made of its most selective S
+// positions with a relaxed threshold; matches become candidate windows for the exact second pass (kmer.h).
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -25,13 +29,12 @@
 namespace smg {
 
 // ---------------------------------------------------------------------------------------------------- build
-// grid.x: prefixes of (W - TAIL) bases, 128 per CTA; grid.y: tiles of 16 motifs of the class.
-//
 // BRANCH AND BOUND: rounded fp32 addition is monotone in each operand, so the score of every k-mer that extends a
 // prefix is bounded by the SAME chain of additions fed with the per-position maxima,
 //     ub = ((acc + max_b T[W-3][b]) + max_b T[W-2][b]) + max_b T[W-1][b]      (fixed order, fp32, every step rounded)
 // -- an exact bound, not an estimate.  At hit densities of 1e-4 .. 6e-3 almost every prefix fails `ub > thr_lo` and its
 // 64 extensions are never formed; the survivors are expanded by the whole warp (lane = extension).
+//
 // Warp-private allocation state of the index build.  Entry slots are reserved kSlotBlock at a time (ONE atomic round trip
 // per block; hits take their slots by ballot + prefix count), and the link of an entry -- the previous head returned by
 // atomicExch -- is stored one emission LATER, so that the round trip of the exchange overlaps the next expansion
