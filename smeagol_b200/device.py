@@ -295,7 +295,8 @@ def choose_index_engines(widths, tc_min_width, total_own, forced_kmer=None, forc
     build against the tcgen05 scan, profiles/r02_bench_widths.txt); kmer_w: widest PRESENT width <= wk (0: no k-mer
     side).  seed_len: 0, or the seed length (11 / 12) when the seed engine is cheaper than the tensor-core prefilter for
     the PWMs on the tensor-core side.  Cost model from the c4 / c2 steps and the per-width matrix: the per-call seed
-    index costs ~1.4e-13 s per (S-mer, column); its scan + exact pass 0.8e-11 s per position + 1.2e-14 s per (position,
+    index costs 0.7e-13 s per (12-mer, column) and 1.4e-13 s per (11-mer, column) -- the bound prunes better on longer
+    k-mers --; its scan + exact pass 0.8e-11 s per position + 1.2e-14 s per (position,
     column) with 12-base seeds, twice that with 11 (candidates double per base the seed loses); the tcgen05 prefilter
     1.1 .. 1.7e-13 s per (position, column).  Seeds win on long scans and lose on short ones."""
     widths = np.asarray(widths)
@@ -316,7 +317,7 @@ def choose_index_engines(widths, tc_min_width, total_own, forced_kmer=None, forc
         for S in range(min(wk, KMER_MAX_WIDTH), SEED_MIN_LEN - 1, -1):
             if nv == 0 or int(tc_w.min()) <= S or int(tc_w.max()) > S + SEED_MAX_REST:
                 continue
-            cost = nv * 4.0 ** S * 1.4e-13 + L * (0.8e-11 + nv * 1.2e-14 * 2.0 ** (KMER_MAX_WIDTH - S))
+            cost = nv * 4.0 ** S * 0.7e-13 * 2.0 ** (KMER_MAX_WIDTH - S) + L * (0.8e-11 + nv * 1.2e-14 * 2.0 ** (KMER_MAX_WIDTH - S))
             if best is None or cost < best[0]:
                 best = (cost, S)
         if forced_seed is not None and nv:
