@@ -273,7 +273,11 @@ def index_scan_roofline(total_bases, n_hits, scan_ms, step_ms, peaks, peaks_kind
             "algorithmic": "bytes per launch = 0.375 B per base (2-bit codes + ambiguity mask) + 12 B per emitted hit (%d hits); "
                            "the kernel is bound by dependent L2 look-ups (bitmap -> list head -> entry) and the hit write-out, "
                            "not by arithmetic: see fp32_pipe_view for the rate in SURVEY 8(d)'s lookup-add units" % n_hits,
-            "peak_source": "MEASURED_PEAKS.json HBM copy bandwidth (%s)" % peaks_kind}
+            "peak_source": "MEASURED_PEAKS.json HBM copy bandwidth (%s)" % peaks_kind,
+            "other_configuration": "SMEAGOL_B200_SEED=0 runs the wide PWMs through the tcgen05 prefilter instead: its tensor side "
+                                   "reaches 0.81 of the sustained bf16 peak (1,166 TFLOP/s algorithmic) but the c4 step takes 37.0 ms "
+                                   "instead of 22.1 (profiles/r02_bench_c4_n1_tcgen05.json) -- a lower roofline fraction on a much "
+                                   "smaller amount of work"}
 
 
 # ------------------------------------------------------------------------------------------------ c4 (headline)
