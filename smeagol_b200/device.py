@@ -386,7 +386,7 @@ class ScanPlan:
                              % (n_out_rows, batch.max_g_len, M))
         self.chunk_len = (pick_chunk_len(batch.total_own, pwmset.n_groups, n_rows=batch.n_rows) if chunk_len is None
                           else int(chunk_len))
-        if chunk_len is None and self.engine in ("hmma", "auto") and self.tc_kind == "tc5":
+        if chunk_len is None and self.engine in ("hmma", "auto") and self.tc_kind in ("tc5", "seed"):  # (seed: it may fall back)
             self.chunk_len = max(512, (self.chunk_len + 511) // 512 * 512)  # the tcgen05 prefilter works in tiles of 512 starts
         chunks = batch.chunks(self.chunk_len)
         self.n_chunks = len(chunks)
@@ -436,8 +436,15 @@ class ScanPlan:
             need = int(ctr[_lib.CTR_KMER_ENTRIES].item())
             if need <= cap:
                 break
-            if need >= (1 << 31) - 1:
-                raise _lib.SmeagolB200Error("seed index too large (threshold too low for the seed engine)")
+            if need > (1 << 27):
+                # a threshold so low that the seeds are not selective (> 2 GB of entries): the tensor-core prefilter takes over
+                self.seed_len, self.tc_kind = 0, os.environ.get("SMEAGOL_B200_TC_KIND", DEFAULT_TC_KIND)
+                self.seed_head = self.seed_entries = None
+                need_cap = int(self.hit_cap * 1.25) + 4096 + (1 << 20)
+                if need_cap > self.cand_cap:
+                    self.cand_cap = need_cap
+                    self.cand = torch.empty(self.cand_cap, dtype=torch.int64, device=dev)
+                return
             cap = min(int(need * 1.1) + 1024, (1 << 31) - 2)
         self.seed_cap, self.seed_n_entries, self._seed_ctr = cap, need, ctr
 
